@@ -1,0 +1,126 @@
+// extern "C" surface of libenflow_b200.so (declared in include/enflow_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "internal.h"
+
+static thread_local char g_err[512] = "";
+
+void enf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* enflow_last_error(void) { return g_err; }
+int enflow_version(void) { return 100; }
+int enflow_hidden(void) { return ENF_H; }
+
+int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts) {
+    if (nf < 1 || nf > ENF_MAX_NF || L < 1 || L > 16) { enf_set_error("param_layout: bad nf=%d or L=%d", nf, L); return -1; }
+    const EgclOffsets eo = enf_egcl_offsets(nf);
+    const ArgmaxOffsets ao = enf_argmax_offsets(nf);
+    int64_t esz[P_EGCL_COUNT], asz[PA_COUNT];
+    enf_egcl_sizes(nf, esz);
+    enf_argmax_sizes(nf, asz);
+    // state_dict order differs from the internal enum order only in naming; list in egcl.py definition order
+    static const int order[P_EGCL_COUNT] = {P_W1, P_B1, P_W2, P_B2, P_W4, P_B4, P_W5, P_B5, P_W3, P_B3, P_WC, P_W6, P_B6, P_W7, P_B7};
+    int idx = 0;
+    for (int l = 0; l < L; ++l)
+        for (int t = 0; t < P_EGCL_COUNT; ++t, ++idx) {
+            if (offsets) offsets[idx] = (int64_t)l * eo.size + eo.off[order[t]];
+            if (counts) counts[idx] = esz[order[t]];
+        }
+    for (int t = 0; t < PA_COUNT; ++t, ++idx) {
+        if (offsets) offsets[idx] = (int64_t)L * eo.size + ao.off[t];
+        if (counts) counts[idx] = asz[t];
+    }
+    return (int64_t)L * eo.size + ao.size;
+}
+
+int64_t enflow_edges_workspace_ints(int N) { return enf_edges_workspace_ints(N); }
+
+int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const float* r_cut, const int* mol_off,
+                       int B, int N, int E_cap, int* row, int* col, int* rowptr, int* ref_pos, int* E_dev,
+                       int* status, int* ws, void* stream) {
+    ENF_CHECK_ARG(B >= 0 && N >= 0 && E_cap >= 0, "build_edges: negative size");
+    if (pos_is_f64)
+        return enf_build_edges_t<double>((const double*)pos, (const double*)box, r_cut, mol_off, B, N, E_cap, row, col,
+                                         rowptr, ref_pos, E_dev, status, ws, ST(stream));
+    return enf_build_edges_t<float>((const float*)pos, (const float*)box, r_cut, mol_off, B, N, E_cap, row, col,
+                                    rowptr, ref_pos, E_dev, status, ws, ST(stream));
+}
+
+int enflow_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
+                          const int* E_dev, int* colptr, int* perm, int* ws, void* stream) {
+    return enf_build_col_perm(col, rowptr, mol_off, B, N, E_cap, E_dev, colptr, perm, ws, ST(stream));
+}
+
+int enflow_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu,
+                          float* out, void* stream) {
+    return enf_segment_sum128(x, ptr, perm, N, E_cap, apply_silu, out, ST(stream));
+}
+int enflow_segment_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int mean, float scale,
+                        int accumulate, float* out, void* stream) {
+    return enf_segment_sum3(x, ptr, perm, N, E_cap, mean, scale, accumulate, out, ST(stream));
+}
+
+int64_t enflow_pack_floats(int nf) { return enf_pack_offsets(nf).size; }
+int enflow_pack_layer(const float* lp, int nf, float* packed, void* stream) {
+    return enf_pack_layer(lp, nf, packed, ST(stream));
+}
+int enflow_node_pre_fwd(const float* h, int N, int nf, const float* lp, float* P, float* S, float* Q, void* stream) {
+    return enf_node_pre_fwd(h, N, nf, lp, P, S, Q, ST(stream));
+}
+int enflow_edge_fwd(const int* row, const int* col, const int* E_dev, int E_cap, const float* pos, const float* box,
+                    const float* P, const float* S, const float* lp, const float* packed, int nf, float* wr,
+                    float* z2, float* z3, float* s, float* trans, void* stream) {
+    return enf_edge_fwd(row, col, E_dev, E_cap, pos, box, P, S, lp, packed, nf, wr, z2, z3, s, trans, ST(stream));
+}
+int enflow_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* lp, const float* packed,
+                         float* z4, float* G, void* stream) {
+    return enf_node_post_fwd(h, agg, N, nf, lp, packed, z4, G, ST(stream));
+}
+
+int enflow_coupling_fwd(const float* Q, const float* F, const float* G, const float* h, const float* g,
+                        const float* pos, const float* vel, const float* box, const int* mol_off, int B, int nf,
+                        float dt, float* h_o, float* g_o, float* pos_o, float* vel_o, float* ldj_mol, void* stream) {
+    return enf_coupling_fwd(Q, F, G, h, g, pos, vel, box, mol_off, B, nf, dt, h_o, g_o, pos_o, vel_o, ldj_mol, ST(stream));
+}
+int enflow_coupling_bwd(const float* Q, const float* vel_in, const float* dldj, int N, int nf, float dt, float* dh,
+                        float* dg, float* dpos, float* dvel, float* dQ, float* dF, float* dG, void* stream) {
+    return enf_coupling_bwd(Q, vel_in, dldj, N, nf, dt, dh, dg, dpos, dvel, dQ, dF, dG, ST(stream));
+}
+int enflow_coupling_inv_pre(const float* g, const float* vel, const float* box, int N, int nf, float dt, float* h,
+                            float* pos, void* stream) {
+    return enf_coupling_inv_pre(g, vel, box, N, nf, dt, h, pos, ST(stream));
+}
+int enflow_coupling_inv_post(const float* Q, const float* F, const float* G, const int* mol_off, int B, int nf,
+                             float dt, float* g, float* vel, float* neg_ldj_mol, void* stream) {
+    return enf_coupling_inv_post(Q, F, G, mol_off, B, nf, dt, g, vel, neg_ldj_mol, ST(stream));
+}
+
+int enflow_argmax_fwd(const float* h, const float* eps, int N, int nf, const float* ap, const int* mol_off, int B,
+                      float* z, float* logq_atom, double* logq_mol, float* log_q, void* stream) {
+    return enf_argmax_fwd(h, eps, N, nf, ap, mol_off, B, z, logq_atom, logq_mol, log_q, ST(stream));
+}
+
+int enflow_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B,
+                   int N, int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj,
+                   double* mol_term, float* loss, void* stream) {
+    return enf_nll_fwd(pos, vel, h, g, mol_off, B, N, nf, max_n, kBT, softening, z_lj, ldj, mol_term, loss, ST(stream));
+}
+int enflow_nll_bwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B,
+                   int nf, int max_n, float kBT, float softening, const float* dloss, float* dpos, float* dvel,
+                   float* dh, float* dg, float* dldj, void* stream) {
+    return enf_nll_bwd(pos, vel, h, g, mol_off, B, nf, max_n, kBT, softening, dloss, dpos, dvel, dh, dg, dldj, ST(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,536 @@
+// K1 (fp32 mode): fused edge kernel of one EGCL (enflow/nn/egcl.py:57-63,71-75,77-89).
+// Per 128-edge tile, without leaving the SM:
+//   d = wrap(pos[row]-pos[col], box/2) (data/base.py:15-19), r = |d|^2 (egcl.py:80)
+//   x1 = silu(P[row] + S[col] + w_r r)          edge_nn.0 via the node-level split (see node.cu)
+//   z2 = W2 x1 + b2, x2 = silu(z2)              edge_nn.2      -> "edge_attr"
+//   z3 = W3 x2 + b3, x3 = silu(z3), s = wc.x3   coord_nn
+//   trans = clamp(d s, +-100)                   egcl.py:72-73
+// z2, z3, s, trans go to HBM (z2/z3 are the saved activations of the fp32-mode backward; K2 reduces
+// silu(z2) and trans per row).  The backward kernel recomputes x1, forms dgrad/wgrad for both dense
+// layers, and emits dz1 (for the node-level scatter) and d(coord_diff).
+//
+// This is the accuracy-first CUDA-core (FFMA) implementation: 1xTF32 on the tensor pipe misses the
+// 1e-5 parity budget.  The dense layers are 128x128x128 register-tiled GEMMs with
+// operands staged in shared memory; activations live feature-major in an XOR-swizzled tile so that
+// both GEMM reads and transposed epilogue stores are bank-conflict free.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TE = ENF_TILE_E;
+constexpr int THREADS = 256;
+constexpr int KC = 32;                       // weight rows per staged chunk
+constexpr int TILE_FLOATS = ENF_H * TE;      // 16384 floats = 64 KB
+
+__device__ __forceinline__ int sw(int f, int m) { return f * TE + (m ^ (((f >> 2) & 7) << 2)); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct EdgeInfo {            // per-tile edge metadata in shared memory
+    int row[TE], col[TE];
+    float d[TE][3];
+    float r[TE];
+    float aux[TE];           // fwd: s ; bwd: ds, then dr
+    float dd[TE][3];         // bwd: direct part of d(coord_diff)
+    int valid[TE];
+};
+
+// thread -> register-tile coordinates for the main GEMMs
+__device__ __forceinline__ int m_of(int ty, int i) { return (i < 4 ? 0 : 64 - 4) + ty * 4 + i; }
+__device__ __forceinline__ int n_of(int tx, int j) { return (j < 4 ? 0 : 64 - 4) + tx * 4 + j; }
+// wgrad coordinates: out[n][k]
+__device__ __forceinline__ int wn_of(int ty, int i) { return ty + 16 * i; }
+__device__ __forceinline__ int wk_of(int tx, int j) { return 4 * (tx & 7) + (tx >> 3) + 2 * (j & 1) + 32 * (j >> 1); }
+
+// acc[i][j] = sum_k A[k][m_i] * Wg[k][n_j];  A: swizzled smem tile, Wg: global [128][128] row-major
+__device__ __forceinline__ void gemm_main(const float* __restrict__ A, const float* __restrict__ Wg, float* Ws,
+                                          float (&acc)[8][8], int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    auto load_chunk = [&](int c) {
+        float* dst = Ws + (c & 1) * (KC * ENF_H);
+        const float* src = Wg + c * (KC * ENF_H);
+#pragma unroll
+        for (int q = 0; q < (KC * ENF_H / 4) / THREADS; ++q) {
+            const int idx = (q * THREADS + tid) * 4;
+            cp_async16(dst + idx, src + idx);
+        }
+        cp_async_commit();
+    };
+    load_chunk(0);
+    constexpr int NC = ENF_H / KC;
+    for (int c = 0; c < NC; ++c) {
+        if (c + 1 < NC) { load_chunk(c + 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float* B = Ws + (c & 1) * (KC * ENF_H);
+#pragma unroll 4
+        for (int kk = 0; kk < KC; ++kk) {
+            const int k = c * KC + kk;
+            const float4 a0 = *reinterpret_cast<const float4*>(A + sw(k, ty * 4));
+            const float4 a1 = *reinterpret_cast<const float4*>(A + sw(k, 64 + ty * 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(B + kk * ENF_H + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(B + kk * ENF_H + 64 + tx * 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+}
+
+// acc[i][j] = sum_e Y[n_i][e] * X[k_j][e]; both swizzled smem tiles
+__device__ __forceinline__ void gemm_wgrad(const float* __restrict__ Y, const float* __restrict__ X,
+                                           float (&acc)[8][8], int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+    for (int e4 = 0; e4 < TE; e4 += 4) {
+        float4 y[8], x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = *reinterpret_cast<const float4*>(Y + sw(wn_of(ty, i), e4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4*>(X + sw(wk_of(tx, j), e4));
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = acc[i][j];
+                a = fmaf(y[i].x, x[j].x, a);
+                a = fmaf(y[i].y, x[j].y, a);
+                a = fmaf(y[i].z, x[j].z, a);
+                a = fmaf(y[i].w, x[j].w, a);
+                acc[i][j] = a;
+            }
+    }
+}
+
+// store a register tile v[m_i][n_j] into a feature-major swizzled smem tile T[n][m]
+__device__ __forceinline__ void store_tile_T(float* T, const float (&v)[8][8], int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = n_of(tx, j);
+        *reinterpret_cast<float4*>(T + sw(n, ty * 4)) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+        *reinterpret_cast<float4*>(T + sw(n, 64 + ty * 4)) = make_float4(v[4][j], v[5][j], v[6][j], v[7][j]);
+    }
+}
+
+__device__ __forceinline__ void load_edge_geometry(EdgeInfo& ei, int t, int e, int E, const int* __restrict__ row,
+                                                   const int* __restrict__ col, const float* __restrict__ pos,
+                                                   const float* __restrict__ box) {
+    const bool ok = e < E;
+    int i = 0, j = 0;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (ok) {
+        i = row[e]; j = col[e];
+        d0 = wrapf_(pos[(int64_t)i * 3 + 0] - pos[(int64_t)j * 3 + 0], 0.5f * box[(int64_t)i * 3 + 0]);
+        d1 = wrapf_(pos[(int64_t)i * 3 + 1] - pos[(int64_t)j * 3 + 1], 0.5f * box[(int64_t)i * 3 + 1]);
+        d2 = wrapf_(pos[(int64_t)i * 3 + 2] - pos[(int64_t)j * 3 + 2], 0.5f * box[(int64_t)i * 3 + 2]);
+    }
+    ei.row[t] = i; ei.col[t] = j; ei.valid[t] = ok;
+    ei.d[t][0] = d0; ei.d[t][1] = d1; ei.d[t][2] = d2;
+    ei.r[t] = d0 * d0 + d1 * d1 + d2 * d2;
+}
+
+// v[i][j] = z1 = P[row][n] + S[col][n] + wr[n] * r   (pre-activation of edge_nn.0); zero for padding rows
+__device__ __forceinline__ void compute_z1(const EdgeInfo& ei, const float* __restrict__ P,
+                                           const float* __restrict__ S, const float* __restrict__ wr,
+                                           float (&v)[8][8], int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+    const float4 w0 = *reinterpret_cast<const float4*>(wr + tx * 4);
+    const float4 w1 = *reinterpret_cast<const float4*>(wr + 64 + tx * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m_of(ty, i);
+        const float r = ei.r[m];
+        const float* p = P + (int64_t)ei.row[m] * ENF_H;
+        const float* s = S + (int64_t)ei.col[m] * ENF_H;
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(p + tx * 4));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(p + 64 + tx * 4));
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + tx * 4));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + 64 + tx * 4));
+        v[i][0] = fmaf(w0.x, r, p0.x + s0.x); v[i][1] = fmaf(w0.y, r, p0.y + s0.y);
+        v[i][2] = fmaf(w0.z, r, p0.z + s0.z); v[i][3] = fmaf(w0.w, r, p0.w + s0.w);
+        v[i][4] = fmaf(w1.x, r, p1.x + s1.x); v[i][5] = fmaf(w1.y, r, p1.y + s1.y);
+        v[i][6] = fmaf(w1.z, r, p1.z + s1.z); v[i][7] = fmaf(w1.w, r, p1.w + s1.w);
+    }
+}
+
+__device__ __forceinline__ void load_rows(const float* __restrict__ Z, int e0, int E, float (&v)[8][8], int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = e0 + m_of(ty, i);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (e < E) {
+            a = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)e * ENF_H + tx * 4));
+            b = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)e * ENF_H + 64 + tx * 4));
+        }
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+        v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+    }
+}
+
+__device__ __forceinline__ void store_rows(float* __restrict__ Z, int e0, int E, const float (&v)[8][8], int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = e0 + m_of(ty, i);
+        if (e < E) {
+            *reinterpret_cast<float4*>(Z + (int64_t)e * ENF_H + tx * 4) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+            *reinterpret_cast<float4*>(Z + (int64_t)e * ENF_H + 64 + tx * 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_vec8(const float* __restrict__ b, float (&o)[8], int tx) {
+    const float4 a = *reinterpret_cast<const float4*>(b + tx * 4);
+    const float4 c = *reinterpret_cast<const float4*>(b + 64 + tx * 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = c.x; o[5] = c.y; o[6] = c.z; o[7] = c.w;
+}
+
+// sum over the 16 threads (tx) that share a row; result valid in every lane of the half-warp
+__device__ __forceinline__ float row_sum16(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(THREADS, 2)
+k_edge_fwd(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ E_dev,
+           const float* __restrict__ pos, const float* __restrict__ box, const float* __restrict__ P,
+           const float* __restrict__ S, const float* __restrict__ wr, const float* __restrict__ W2T,
+           const float* __restrict__ b2, const float* __restrict__ W3T, const float* __restrict__ b3,
+           const float* __restrict__ wc, float* __restrict__ z2, float* __restrict__ z3, float* __restrict__ s_out,
+           float* __restrict__ trans) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* XT = reinterpret_cast<float*>(smem_raw);
+    float* Ws = XT + TILE_FLOATS;
+    EdgeInfo& ei = *reinterpret_cast<EdgeInfo*>(Ws + 2 * KC * ENF_H);
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int E = E_dev[0];
+    const int tiles = (E + TE - 1) / TE;
+    float bias2[8], bias3[8], wcv[8];
+    load_vec8(b2, bias2, tx);
+    load_vec8(b3, bias3, tx);
+    load_vec8(wc, wcv, tx);
+    float acc[8][8];
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * TE;
+        __syncthreads();
+        if (tid < TE) load_edge_geometry(ei, tid, e0 + tid, E, row, col, pos, box);
+        __syncthreads();
+        compute_z1(ei, P, S, wr, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = ei.valid[m_of(ty, i)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = ok ? siluf_(acc[i][j]) : 0.f;
+        }
+        store_tile_T(XT, acc, tid);
+        __syncthreads();
+        gemm_main(XT, W2T, Ws, acc, tid);           // ends with __syncthreads(): XT is free
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] += bias2[j];
+        store_rows(z2, e0, E, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = ei.valid[m_of(ty, i)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = ok ? siluf_(acc[i][j]) : 0.f;
+        }
+        store_tile_T(XT, acc, tid);
+        __syncthreads();
+        gemm_main(XT, W3T, Ws, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] += bias3[j];
+        store_rows(z3, e0, E, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float p = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p = fmaf(wcv[j], siluf_(acc[i][j]), p);
+            p = row_sum16(p);
+            if (tx == 0) ei.aux[m_of(ty, i)] = p;
+        }
+        __syncthreads();
+        if (tid < TE && ei.valid[tid]) {
+            const int e = e0 + tid;
+            const float s = ei.aux[tid];
+            s_out[e] = s;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) trans[(int64_t)e * 3 + c] = fminf(fmaxf(ei.d[tid][c] * s, -100.f), 100.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// Per-CTA partial layout (floats): dW2 [H*H] | dW3 [H*H] | db2 [H] | db3 [H] | dwc [H] | dwr [H]
+constexpr int EDGE_PARTIAL = 2 * ENF_H * ENF_H + 4 * ENF_H;
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_edge_bwd(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ rowptr,
+           const int* __restrict__ E_dev, const float* __restrict__ pos, const float* __restrict__ box,
+           const float* __restrict__ P, const float* __restrict__ S, const float* __restrict__ wr,
+           const float* __restrict__ W2, const float* __restrict__ W3, const float* __restrict__ wc,
+           const float* __restrict__ z2, const float* __restrict__ z3, const float* __restrict__ s_saved,
+           const float* __restrict__ dagg, const float* __restrict__ dF, float coords_weight,
+           float* __restrict__ dz1, float* __restrict__ dd_out, float* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* XT = reinterpret_cast<float*>(smem_raw);
+    float* YT = XT + TILE_FLOATS;
+    float* Ws = YT + TILE_FLOATS;
+    EdgeInfo& ei = *reinterpret_cast<EdgeInfo*>(Ws + 2 * KC * ENF_H);
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int E = E_dev[0];
+    const int tiles = (E + TE - 1) / TE;
+    float* my = partial + (int64_t)blockIdx.x * EDGE_PARTIAL;
+    float* pW2 = my;
+    float* pW3 = my + ENF_H * ENF_H;
+    float wcv[8], wrv[8];
+    load_vec8(wc, wcv, tx);
+    load_vec8(wr, wrv, tx);
+    float gb2[8], gb3[8], gwc[8], gwr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gb2[j] = gb3[j] = gwc[j] = gwr[j] = 0.f;
+    float acc[8][8], t[8][8];
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * TE;
+        __syncthreads();
+        if (tid < TE) {
+            const int e = e0 + tid;
+            load_edge_geometry(ei, tid, e, E, row, col, pos, box);
+            float ds = 0.f, dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+            if (e < E) {
+                const int i = ei.row[tid];
+                const int deg = rowptr[i + 1] - rowptr[i];
+                const float sc = coords_weight / (float)(deg > 1 ? deg : 1);     // helpers.py:70 (Q12)
+                const float s = s_saved[e];
+                float dtr[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float tr = ei.d[tid][c] * s;
+                    const bool pass = (tr >= -100.f) && (tr <= 100.f);          // clamp backward mask
+                    dtr[c] = pass ? dF[(int64_t)i * 3 + c] * sc : 0.f;
+                    ds = fmaf(dtr[c], ei.d[tid][c], ds);
+                }
+                dd0 = dtr[0] * s; dd1 = dtr[1] * s; dd2 = dtr[2] * s;
+            }
+            ei.aux[tid] = ds;
+            ei.dd[tid][0] = dd0; ei.dd[tid][1] = dd1; ei.dd[tid][2] = dd2;
+        }
+        __syncthreads();
+        // ---- coord_nn backward head: dz3 = ds * wc * silu'(z3) ; x2 = silu(z2)
+        load_rows(z3, e0, E, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float ds = ei.aux[m_of(ty, i)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float z = acc[i][j];
+                const float sg = sigmoidf_(z);
+                gwc[j] = fmaf(ds, z * sg, gwc[j]);
+                const float dz = ds * wcv[j] * (sg * (1.0f + z * (1.0f - sg)));
+                gb3[j] += dz;
+                acc[i][j] = dz;
+            }
+        }
+        store_tile_T(YT, acc, tid);
+        load_rows(z2, e0, E, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = siluf_(acc[i][j]);     // silu(0) = 0 for padding rows
+        store_tile_T(XT, acc, tid);
+        __syncthreads();
+        // ---- dW3 += dz3^T x2
+        gemm_wgrad(YT, XT, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pW3[wn_of(ty, i) * ENF_H + wk_of(tx, j)] += acc[i][j];
+        // ---- dx2 = dz3 W3 + dagg[row] ; dz2 = dx2 * silu'(z2)
+        gemm_main(YT, W3, Ws, acc, tid);            // ends with __syncthreads(): YT and XT reads are done
+        load_rows(z2, e0, E, t, tid);               // re-read (L2 hit) instead of holding 64 registers live
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m_of(ty, i);
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            if (ei.valid[m]) {
+                const float* da = dagg + (int64_t)ei.row[m] * ENF_H;
+                a0 = __ldg(reinterpret_cast<const float4*>(da + tx * 4));
+                a1 = __ldg(reinterpret_cast<const float4*>(da + 64 + tx * 4));
+            }
+            const float add[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dz = (acc[i][j] + add[j]) * dsiluf_(t[i][j]);
+                gb2[j] += dz;
+                acc[i][j] = dz;
+            }
+        }
+        store_tile_T(YT, acc, tid);
+        // ---- recompute x1
+        compute_z1(ei, P, S, wr, t, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = ei.valid[m_of(ty, i)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = ok ? siluf_(t[i][j]) : 0.f;
+        }
+        store_tile_T(XT, acc, tid);
+        __syncthreads();
+        // ---- dW2 += dz2^T x1
+        gemm_wgrad(YT, XT, acc, tid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pW2[wn_of(ty, i) * ENF_H + wk_of(tx, j)] += acc[i][j];
+        // ---- dx1 = dz2 W2 ; dz1 = dx1 * silu'(z1)
+        gemm_main(YT, W2, Ws, acc, tid);
+        compute_z1(ei, P, S, wr, t, tid);           // recomputed for silu'(z1); P/S rows are L1/L2 hits
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m_of(ty, i);
+            const float r = ei.r[m];
+            const bool ok = ei.valid[m];
+            float dr = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dz = ok ? acc[i][j] * dsiluf_(t[i][j]) : 0.f;
+                acc[i][j] = dz;
+                gwr[j] = fmaf(dz, r, gwr[j]);
+                dr = fmaf(wrv[j], dz, dr);
+            }
+            dr = row_sum16(dr);
+            if (tx == 0) ei.aux[m] = dr;
+        }
+        store_rows(dz1, e0, E, acc, tid);
+        __syncthreads();
+        if (tid < TE && ei.valid[tid]) {
+            const int e = e0 + tid;
+            const float dr2 = 2.0f * ei.aux[tid];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dd_out[(int64_t)e * 3 + c] = fmaf(dr2, ei.d[tid][c], ei.dd[tid][c]);
+        }
+    }
+    // ---- column sums: combine the 16 row groups (ty) in fixed order through shared memory
+    __syncthreads();
+    float* red = XT;    // [4][16][128]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = n_of(tx, j);
+        red[(0 * 16 + ty) * ENF_H + n] = gb2[j];
+        red[(1 * 16 + ty) * ENF_H + n] = gb3[j];
+        red[(2 * 16 + ty) * ENF_H + n] = gwc[j];
+        red[(3 * 16 + ty) * ENF_H + n] = gwr[j];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 4 * ENF_H; idx += THREADS) {
+        const int a = idx / ENF_H, n = idx % ENF_H;
+        float s = 0.f;
+        for (int y = 0; y < 16; ++y) s += red[(a * 16 + y) * ENF_H + n];
+        my[2 * ENF_H * ENF_H + idx] = s;
+    }
+}
+
+// grad[dst] += sum over CTAs (fixed order)
+__global__ void k_edge_reduce(const float* __restrict__ partial, int n_cta, int o_w2, int o_w3, int o_b2, int o_b3,
+                              int o_wc, int o_w1, int e1, float* __restrict__ grad) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= EDGE_PARTIAL) return;
+    float acc = 0.f;
+    for (int c = 0; c < n_cta; ++c) acc += partial[(int64_t)c * EDGE_PARTIAL + idx];
+    const int HH = ENF_H * ENF_H;
+    int dst;
+    if (idx < HH) dst = o_w2 + idx;
+    else if (idx < 2 * HH) dst = o_w3 + (idx - HH);
+    else if (idx < 2 * HH + ENF_H) dst = o_b2 + (idx - 2 * HH);
+    else if (idx < 2 * HH + 2 * ENF_H) dst = o_b3 + (idx - 2 * HH - ENF_H);
+    else if (idx < 2 * HH + 3 * ENF_H) dst = o_wc + (idx - 2 * HH - 2 * ENF_H);
+    else dst = o_w1 + (idx - 2 * HH - 3 * ENF_H) * e1 + (e1 - 1);     // w_r = last column of edge_nn.0.weight
+    grad[dst] += acc;
+}
+
+__global__ void k_extract_wr(const float* __restrict__ W1, int e1, float* __restrict__ wr) {
+    const int k = threadIdx.x;
+    wr[k] = W1[k * e1 + e1 - 1];
+}
+
+}  // namespace
+
+static size_t fwd_smem() { return sizeof(float) * (TILE_FLOATS + 2 * KC * ENF_H) + sizeof(EdgeInfo); }
+static size_t bwd_smem() { return sizeof(float) * (2 * TILE_FLOATS + 2 * KC * ENF_H) + sizeof(EdgeInfo); }
+
+int enf_edge_fwd_grid() { return enf_num_sms() * 2; }
+int enf_edge_bwd_grid() { return enf_num_sms(); }
+int64_t enf_edge_partial_floats() { return (int64_t)enf_edge_bwd_grid() * EDGE_PARTIAL; }
+
+// wr: [H] scratch holding the w_r column of edge_nn.0.weight (extracted here)
+int enf_edge_fwd(const int* row, const int* col, const int* E_dev, int E_cap, const float* pos, const float* box,
+                 const float* P, const float* S, const float* lp, const float* packed, int nf, float* wr, float* z2,
+                 float* z3, float* s_out, float* trans, cudaStream_t st) {
+    if (E_cap == 0) return ENF_OK;
+    const EgclOffsets o = enf_egcl_offsets(nf);
+    const PackOffsets p = enf_pack_offsets(nf);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_edge_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem());
+        attr = true;
+    }
+    k_extract_wr<<<1, ENF_H, 0, st>>>(lp + o.off[P_W1], 2 * nf + 1, wr);
+    int grid = (E_cap + TE - 1) / TE;
+    if (grid > enf_edge_fwd_grid()) grid = enf_edge_fwd_grid();
+    k_edge_fwd<<<grid, THREADS, fwd_smem(), st>>>(row, col, E_dev, pos, box, P, S, wr, packed + p.w2t,
+                                                  lp + o.off[P_B2], packed + p.w3t, lp + o.off[P_B3],
+                                                  lp + o.off[P_WC], z2, z3, s_out, trans);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
+int enf_edge_bwd(const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap, const float* pos,
+                 const float* box, const float* P, const float* S, const float* lp, int nf, float* wr,
+                 const float* z2, const float* z3, const float* s_saved, const float* dagg, const float* dF,
+                 float coords_weight, float* dz1, float* dd, float* lgrad, float* partial, cudaStream_t st) {
+    if (E_cap == 0) return ENF_OK;
+    const EgclOffsets o = enf_egcl_offsets(nf);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_edge_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem());
+        attr = true;
+    }
+    const int grid = enf_edge_bwd_grid();
+    cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * EDGE_PARTIAL, st);
+    k_extract_wr<<<1, ENF_H, 0, st>>>(lp + o.off[P_W1], 2 * nf + 1, wr);
+    k_edge_bwd<<<grid, THREADS, bwd_smem(), st>>>(row, col, rowptr, E_dev, pos, box, P, S, wr, lp + o.off[P_W2],
+                                                  lp + o.off[P_W3], lp + o.off[P_WC], z2, z3, s_saved, dagg, dF,
+                                                  coords_weight, dz1, dd, partial);
+    k_edge_reduce<<<(EDGE_PARTIAL + 255) / 256, 256, 0, st>>>(partial, grid, (int)o.off[P_W2], (int)o.off[P_W3],
+                                                              (int)o.off[P_B2], (int)o.off[P_B3], (int)o.off[P_WC],
+                                                              (int)o.off[P_W1], 2 * nf + 1, lgrad);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}

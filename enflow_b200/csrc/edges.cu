@@ -1,0 +1,326 @@
+// K0: neighbour-list construction, bit-exact with the reference's Data.edges
+// (enflow/data/base.py:122-144 + enflow/utils/helpers.py:15-29), including its quirks:
+//   Q6  both columns of the (image point, atom) hit list are remapped through id_mapping
+//   Q7  image pre-filter: sum((p/(box+r_cut))^2) <= 1, radii = box + r_cut
+//   Q9  r_cut is float32; r_cut*r_cut is an fp32 product compared (strict <) against fp64 d^2
+//   Q10 image order c outer / b / a inner over [-L,+L,0]; Q11 self pairs dropped on remapped labels.
+// All geometry is evaluated in fp64 with explicit round-to-nearest ops (no FMA contraction) so the
+// comparisons agree with ATen's CPU results bit for bit on identical inputs.
+//
+// Output order: the hot path wants edges grouped by row (CSR) so segment reductions have a fixed
+// order; the reference order (surviving image point, atom) is recoverable through ref_pos[e].
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ double ld3(const T* p, int i, int c) { return (double)p[(int64_t)i * 3 + c]; }
+
+__device__ __forceinline__ double shift_of(int idx, double L) {   // helpers.py:17: [-L, +L, 0]
+    return idx == 0 ? -L : (idx == 1 ? L : 0.0);
+}
+
+__global__ void k_atom_mol(const int* __restrict__ mol_off, int B, int* __restrict__ atom_mol) {
+    int m = blockIdx.x;
+    if (m >= B) return;
+    for (int i = mol_off[m] + threadIdx.x; i < mol_off[m + 1]; i += blockDim.x) atom_mol[i] = m;
+}
+
+// One CTA per molecule: survivor flags of the 27n image points, ranked in (image, atom) order.
+template <typename T>
+__global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ pos, const T* __restrict__ box,
+                                                          const float* __restrict__ r_cut,
+                                                          const int* __restrict__ mol_off, int B,
+                                                          int* __restrict__ qrank, int* __restrict__ idmap,
+                                                          int* __restrict__ nsurv) {
+    __shared__ int warp_tot[8];
+    __shared__ int running_s;
+    const int m = blockIdx.x;
+    const int o = mol_off[m], n = mol_off[m + 1] - o;
+    const int64_t base = 27LL * o;
+    const double rc = (double)r_cut[m];
+    const double bx = ld3(box, o, 0), by = ld3(box, o, 1), bz = ld3(box, o, 2);   // base.py:130 box[0]
+    const double ex = __dadd_rn(bx, rc), ey = __dadd_rn(by, rc), ez = __dadd_rn(bz, rc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running_s = 0;
+    __syncthreads();
+    const int total = 27 * n;
+    for (int start = 0; start < total; start += 256) {
+        const int ip = start + threadIdx.x;
+        bool keep = false;
+        int a = 0;
+        if (ip < total) {
+            const int k = ip / n;
+            a = ip - k * n;
+            const double px = __dadd_rn(ld3(pos, o + a, 0), shift_of(k % 3, bx));
+            const double py = __dadd_rn(ld3(pos, o + a, 1), shift_of((k / 3) % 3, by));
+            const double pz = __dadd_rn(ld3(pos, o + a, 2), shift_of(k / 9, bz));
+            const double sx = __ddiv_rn(px, ex), sy = __ddiv_rn(py, ey), sz = __ddiv_rn(pz, ez);
+            const double q = __dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz));
+            keep = q <= 1.0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int pre = running_s;
+        for (int w = 0; w < wid; ++w) pre += warp_tot[w];
+        const int rank = pre + __popc(bal & ((1u << lane) - 1u));
+        if (ip < total) {
+            qrank[base + ip] = keep ? rank : -1;
+            if (keep) idmap[base + rank] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += warp_tot[w];
+            running_s += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) nsurv[m] = running_s;
+}
+
+// One warp per (global atom i, image k). FILL=false counts hits, FILL=true writes them.
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, const T* __restrict__ box,
+                                                     const float* __restrict__ r_cut,
+                                                     const int* __restrict__ mol_off, const int* __restrict__ atom_mol,
+                                                     int N, const int* __restrict__ qrank,
+                                                     const int* __restrict__ idmap, const int* __restrict__ nsurv,
+                                                     int* __restrict__ cnt_csr, int* __restrict__ cnt_ref,
+                                                     int* __restrict__ row, int* __restrict__ col,
+                                                     int* __restrict__ ref_pos, int* __restrict__ rowptr, int E_cap,
+                                                     int* __restrict__ status) {
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= 27LL * N) return;
+    const int i = (int)(gw / 27), k = (int)(gw - 27LL * i);
+    const int m = atom_mol[i];
+    const int o = mol_off[m], n = mol_off[m + 1] - o, a = i - o;
+    const int64_t base = 27LL * o;
+    const int64_t ip = base + (int64_t)k * n + a;
+    if (FILL && k == 0 && lane == 0) rowptr[i] = cnt_csr[gw];
+    const int q = qrank[ip];
+    if (q < 0) {
+        if (!FILL && lane == 0) { cnt_csr[gw] = 0; cnt_ref[ip] = 0; }
+        return;
+    }
+    const double bx = ld3(box, o, 0), by = ld3(box, o, 1), bz = ld3(box, o, 2);
+    const double px = __dadd_rn(ld3(pos, i, 0), shift_of(k % 3, bx));
+    const double py = __dadd_rn(ld3(pos, i, 1), shift_of((k / 3) % 3, by));
+    const double pz = __dadd_rn(ld3(pos, i, 2), shift_of(k / 9, bz));
+    const float rcf = r_cut[m];
+    const double r_sq = (double)__fmul_rn(rcf, rcf);          // base.py:133, fp32 product (Q9)
+    const int ns = nsurv[m];
+    int running = 0;
+    int out_csr = 0, out_ref = 0;
+    if (FILL) { out_csr = cnt_csr[gw]; out_ref = cnt_ref[ip]; }
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        int lab = 0;
+        if (j < n) {
+            const double dx = __dsub_rn(px, ld3(pos, o + j, 0));
+            const double dy = __dsub_rn(py, ld3(pos, o + j, 1));
+            const double dz = __dsub_rn(pz, ld3(pos, o + j, 2));
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 < r_sq) {
+                // base.py:137: the atom column is ALSO indexed through id_mapping (Q6)
+                if (j < ns) lab = idmap[base + j];
+                else { lab = j; atomicOr(status, 2); }        // the reference would raise IndexError here
+                hit = lab != a;                                 // base.py:139 (Q11)
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) {
+            const int r = running + __popc(bal & ((1u << lane) - 1u));
+            const int e = out_csr + r;
+            if (e < E_cap) { row[e] = i; col[e] = o + lab; if (ref_pos) ref_pos[e] = out_ref + r; }
+        }
+        running += __popc(bal);
+    }
+    if (!FILL && lane == 0) { cnt_csr[gw] = running; cnt_ref[ip] = running; }
+}
+
+// ---- exclusive scan of two int arrays of equal length (blockIdx.y selects the array) ----
+constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_CHUNK = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ int block_exclusive(int v, int* total) {
+    __shared__ int wsum[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) { if (w < wid) pre += wsum[w]; tot += wsum[w]; }
+    __syncthreads();
+    *total = tot;
+    return pre + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const int* a0, const int* a1, int64_t n, int* sums, int nb) {
+    const int* a = blockIdx.y ? a1 : a0;
+    const int64_t b0 = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) if (b0 + t < n) s += a[b0 + t];
+    int tot;
+    block_exclusive(s, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.y * nb + blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(int* sums, int nb) {
+    int* s = sums + blockIdx.y * nb;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int start = 0; start < nb; start += SCAN_THREADS) {
+        const int i = start + threadIdx.x;
+        const int v = i < nb ? s[i] : 0;
+        int tot;
+        const int ex = block_exclusive(v, &tot);
+        const int c = carry;
+        if (i < nb) s[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+
+// in place; element n (one past the end) receives the grand total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int* a0, int* a1, int64_t n, const int* sums, int nb) {
+    int* a = blockIdx.y ? a1 : a0;
+    const int64_t b0 = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) { v[t] = (b0 + t < n) ? a[b0 + t] : 0; s += v[t]; }
+    int tot;
+    int ex = block_exclusive(s, &tot) + sums[blockIdx.y * nb + blockIdx.x];
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        if (b0 + t < n) a[b0 + t] = ex;
+        ex += v[t];
+        if (b0 + t == n - 1) a[n] = ex;
+    }
+}
+
+__global__ void k_edges_finish(const int* __restrict__ cnt_csr, int N, int E_cap, int* __restrict__ rowptr,
+                               int* __restrict__ E_dev, int* __restrict__ status) {
+    const int E = cnt_csr[27LL * N];
+    rowptr[N] = E;
+    E_dev[0] = E < E_cap ? E : E_cap;
+    E_dev[1] = E;
+    if (E > E_cap) atomicOr(status, 1);
+}
+
+// ---- column-grouped permutation (CSR -> CSC), deterministic and stable in edge order ----
+__global__ void k_col_count(const int* __restrict__ col, const int* __restrict__ E_dev, int* __restrict__ colcnt) {
+    const int E = E_dev[0];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
+        atomicAdd(&colcnt[col[e]], 1);       // integer adds: the result does not depend on order
+}
+
+// one CTA per molecule; chunks of 256 edges; rank among equal columns by comparison in smem
+__global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, const int* __restrict__ rowptr,
+                                                   const int* __restrict__ mol_off, const int* __restrict__ colptr,
+                                                   int* __restrict__ cursor, int* __restrict__ perm, int E_cap) {
+    __shared__ int ccol[256];
+    const int m = blockIdx.x;
+    const int e_begin = rowptr[mol_off[m]];
+    int e_end = rowptr[mol_off[m + 1]];
+    if (e_end > E_cap) e_end = E_cap;
+    for (int e0 = e_begin; e0 < e_end; e0 += 256) {
+        const int e = e0 + threadIdx.x;
+        const int c = e < e_end ? col[e] : -1;
+        ccol[threadIdx.x] = c;
+        __syncthreads();
+        int before = 0, after = 0;
+        if (c >= 0) {
+            for (int t = 0; t < 256; ++t) {
+                const bool same = ccol[t] == c;
+                before += (same && t < threadIdx.x);
+                after += (same && t > threadIdx.x);
+            }
+            perm[colptr[c] + cursor[c] + before] = e;
+        }
+        __syncthreads();
+        if (c >= 0 && after == 0) cursor[c] += before + 1;   // exactly one thread per distinct column
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+static int scan2(int* a0, int* a1, int64_t n, int* sums, cudaStream_t st) {
+    const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    dim3 g(nb, 2);
+    k_scan_sums<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
+    k_scan_top<<<dim3(1, 2), SCAN_THREADS, 0, st>>>(sums, nb);
+    k_scan_apply<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
+int64_t enf_edges_workspace_ints(int N) {
+    const int64_t n27 = 27LL * N;
+    const int64_t nb = (n27 + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    // qrank, idmap, cnt_csr(+1), cnt_ref(+1), nsurv(<=N), atom_mol(N), colcnt(N+1), cursor(N), scan sums
+    return 4 * n27 + 2 + 4LL * N + 1 + 2 * nb + 64;
+}
+
+template <typename T>
+int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int* mol_off, int B, int N, int E_cap,
+                      int* row, int* col, int* rowptr, int* ref_pos, int* E_dev, int* status, int* ws,
+                      cudaStream_t st) {
+    const int64_t n27 = 27LL * N;
+    int* qrank = ws;
+    int* idmap = qrank + n27;
+    int* cnt_csr = idmap + n27;
+    int* cnt_ref = cnt_csr + n27 + 1;
+    int* nsurv = cnt_ref + n27 + 1;
+    int* atom_mol = nsurv + N;
+    int* sums = atom_mol + N + (2 * N + 1);   // colcnt/cursor live between (see enf_build_col_perm)
+    k_atom_mol<<<B, 128, 0, st>>>(mol_off, B, atom_mol);
+    k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv);
+    const int64_t warps = n27;
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    k_edges_hits<T, false><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
+                                                   cnt_ref, nullptr, nullptr, nullptr, nullptr, E_cap, status);
+    ENF_CHECK_LAUNCH();
+    ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
+    k_edges_hits<T, true><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
+                                                  cnt_ref, row, col, ref_pos, rowptr, E_cap, status);
+    k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
+template int enf_build_edges_t<float>(const float*, const float*, const float*, const int*, int, int, int, int*, int*,
+                                      int*, int*, int*, int*, int*, cudaStream_t);
+template int enf_build_edges_t<double>(const double*, const double*, const float*, const int*, int, int, int, int*,
+                                       int*, int*, int*, int*, int*, int*, cudaStream_t);
+
+// colptr [N+1], perm [E_cap]; ws is the same workspace handed to enf_build_edges_t (its atom_mol is reused)
+int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
+                       const int* E_dev, int* colptr, int* perm, int* ws, cudaStream_t st) {
+    const int64_t n27 = 27LL * N;
+    int* after_atom_mol = ws + 4 * n27 + 2 + 2LL * N;
+    int* cursor = after_atom_mol;            // N
+    int* dummy = cursor + N;                 // second array for scan2 (N+1)
+    int* sums = dummy + N + 1;
+    cudaMemsetAsync(colptr, 0, sizeof(int) * (N + 1), st);
+    cudaMemsetAsync(cursor, 0, sizeof(int) * (2LL * N + 1), st);
+    k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr);
+    ENF_CHECK_LAUNCH();
+    ENF_TRY(scan2(colptr, dummy, N, sums, st));
+    cudaMemsetAsync(cursor, 0, sizeof(int) * N, st);
+    k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}

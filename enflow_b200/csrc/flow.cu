@@ -1,0 +1,237 @@
+// Whole-pass orchestration: LFIntegrator.forward, its backward, and LFIntegrator.reverse
+// (enflow/flow/dynamics.py:10-37) as one stream-ordered sequence of kernel launches per call.
+// No allocation and no host synchronisation happen here: the caller provides one workspace that is
+// carved deterministically from the dims, and data-dependent sizes (edge counts) stay on the device.
+#include "internal.h"
+
+struct enflow_dims_t {
+    int32_t B, N, nf, L, E_cap, max_n;
+    float dt, coords_weight;
+};
+
+namespace {
+
+struct Bump {
+    char* base;
+    size_t off;
+    explicit Bump(void* p) : base(reinterpret_cast<char*>(p)), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) / 256 * 256;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct LayerSave {           // kept per layer when training
+    int *row, *col, *rowptr, *E_dev;
+    float *Q, *z2, *z3, *s, *agg, *z4;
+};
+
+struct Workspace {
+    // states[l] = node state entering layer l; states[L] only when training is off is the output itself
+    float *h[17], *g[17], *pos[17], *vel[17];
+    LayerSave layer[16];
+    float* packed;           // L * pack size
+    float *P, *S, *F, *G, *trans, *wr;
+    int* edges_ws;
+    float* logq_atom;
+    double* logq_mol;
+    float* log_q;
+    // backward scratch
+    float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd, *partial, *Qscratch;
+    int *colptr, *perm;
+    size_t bytes;
+};
+
+size_t partial_floats(const enflow_dims_t& d) {
+    size_t m = (size_t)enf_edge_partial_floats();
+    size_t a = (size_t)enf_node_post_partial_floats(d.N, d.nf);
+    if (a > m) m = a;
+    a = (size_t)enf_node_pre_partial_floats(d.N, d.nf);
+    if (a > m) m = a;
+    a = (size_t)enf_argmax_partial_floats(d.N, d.nf);
+    if (a > m) m = a;
+    return m;
+}
+
+Workspace carve(const enflow_dims_t& d, void* base, int training) {
+    Workspace w;
+    Bump b(base);
+    const size_t N = d.N, nf = d.nf, E = d.E_cap, H = ENF_H;
+    const int saved_layers = training ? d.L : 1;
+    const int nstates = training ? d.L : 2;        // inference ping-pongs between two buffers
+    for (int l = 0; l < nstates; ++l) {
+        w.h[l] = b.take<float>(N * nf); w.g[l] = b.take<float>(N * nf);
+        w.pos[l] = b.take<float>(N * 3); w.vel[l] = b.take<float>(N * 3);
+    }
+    for (int l = 0; l < saved_layers; ++l) {
+        LayerSave& s = w.layer[l];
+        s.row = b.take<int>(E); s.col = b.take<int>(E); s.rowptr = b.take<int>(N + 1); s.E_dev = b.take<int>(2);
+        s.Q = b.take<float>(N); s.z2 = b.take<float>(E * H); s.z3 = b.take<float>(E * H); s.s = b.take<float>(E);
+        s.agg = b.take<float>(N * H); s.z4 = b.take<float>(N * H);
+    }
+    w.packed = b.take<float>((size_t)d.L * enf_pack_offsets(d.nf).size);
+    w.P = b.take<float>(N * H); w.S = b.take<float>(N * H);
+    w.F = b.take<float>(N * 3); w.G = b.take<float>(N * nf);
+    w.trans = b.take<float>(E * 3); w.wr = b.take<float>(H);
+    w.edges_ws = b.take<int>((size_t)enf_edges_workspace_ints(d.N));
+    w.logq_atom = b.take<float>(N); w.logq_mol = b.take<double>(d.B); w.log_q = b.take<float>(1);
+    if (training) {
+        w.dQ = b.take<float>(N); w.dF = b.take<float>(N * 3); w.dG = b.take<float>(N * nf);
+        w.dagg = b.take<float>(N * H); w.dP = b.take<float>(N * H); w.dS = b.take<float>(N * H);
+        w.dz1 = b.take<float>(E * H); w.dd = b.take<float>(E * 3);
+        w.partial = b.take<float>(partial_floats(d));
+        w.Qscratch = b.take<float>(N);
+        w.colptr = b.take<int>(N + 1); w.perm = b.take<int>(E);
+    }
+    w.bytes = (b.off + 255) / 256 * 256;
+    return w;
+}
+
+int check_dims(const enflow_dims_t* d) {
+    ENF_CHECK_ARG(d != nullptr, "dims is NULL");
+    ENF_CHECK_ARG(d->nf >= 1 && d->nf <= ENF_MAX_NF, "nf=%d outside [1,%d]", d->nf, ENF_MAX_NF);
+    ENF_CHECK_ARG(d->L >= 1 && d->L <= 16, "L=%d outside [1,16]", d->L);
+    ENF_CHECK_ARG(d->B >= 0 && d->N >= 0 && d->E_cap >= 0, "negative size");
+    return ENF_OK;
+}
+
+const float* layer_params(const float* params, int nf, int l) { return params + (int64_t)l * enf_egcl_offsets(nf).size; }
+float* layer_params(float* params, int nf, int l) { return params + (int64_t)l * enf_egcl_offsets(nf).size; }
+const float* argmax_params(const float* params, int nf, int L) { return params + (int64_t)L * enf_egcl_offsets(nf).size; }
+float* argmax_params(float* params, int nf, int L) { return params + (int64_t)L * enf_egcl_offsets(nf).size; }
+
+void copy_f(float* dst, const float* src, size_t n, cudaStream_t st) {
+    if (dst != src && n) cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+}
+
+// Q, F, G of one EGCL at the given node state (egcl.py:77-93); saves activations into `sv`
+int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv, const float* lp, const float* packed,
+                 const float* h, const float* pos, const float* box, const float* r_cut, const int* mol_off,
+                 int* status, cudaStream_t st) {
+    ENF_TRY(enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
+                                     sv.E_dev, status, w.edges_ws, st));
+    ENF_TRY(enf_node_pre_fwd(h, d.N, d.nf, lp, w.P, w.S, sv.Q, st));
+    ENF_TRY(enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr, sv.z2, sv.z3,
+                         sv.s, w.trans, st));
+    ENF_TRY(enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
+    ENF_TRY(enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
+    ENF_TRY(enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
+    return ENF_OK;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" size_t enflow_flow_workspace_bytes(const enflow_dims_t* dims, int training) {
+    if (check_dims(dims) != ENF_OK) return 0;
+    return carve(*dims, nullptr, training).bytes;
+}
+
+extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* params, const float* h_in,
+                                   const float* g_in, const float* pos_in, const float* vel_in, const float* box,
+                                   const float* r_cut, const int* mol_off, const float* eps, void* workspace,
+                                   size_t workspace_bytes, int training, float* h_out, float* g_out, float* pos_out,
+                                   float* vel_out, float* ldj_mol, float* ldj, int* status, void* stream) {
+    ENF_TRY(check_dims(dims));
+    const enflow_dims_t& d = *dims;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace w = carve(d, workspace, training);
+    ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+    const int nf = d.nf;
+    const size_t N = d.N;
+    cudaMemsetAsync(ldj_mol, 0, sizeof(float) * d.B, st);
+    for (int l = 0; l < d.L; ++l)
+        ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
+    // state entering layer 0: dequantised h (dynamics.py:11), everything else copied
+    if (eps) {
+        ENF_TRY(enf_argmax_fwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), mol_off, d.B, w.h[0], w.logq_atom,
+                               w.logq_mol, w.log_q, st));
+    } else {
+        copy_f(w.h[0], h_in, N * nf, st);
+    }
+    copy_f(w.g[0], g_in, N * nf, st);
+    copy_f(w.pos[0], pos_in, N * 3, st);
+    copy_f(w.vel[0], vel_in, N * 3, st);
+    for (int l = 0; l < d.L; ++l) {
+        const int cur = training ? l : (l & 1);
+        const bool last = l == d.L - 1;
+        const int nxt = training ? l + 1 : ((l + 1) & 1);
+        float* ho = last ? h_out : w.h[nxt];
+        float* go = last ? g_out : w.g[nxt];
+        float* po = last ? pos_out : w.pos[nxt];
+        float* vo = last ? vel_out : w.vel[nxt];
+        const LayerSave& sv = w.layer[training ? l : 0];
+        ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
+                             w.h[cur], w.pos[cur], box, r_cut, mol_off, status, st));
+        ENF_TRY(enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
+                                 ho, go, po, vo, ldj_mol, st));
+    }
+    ENF_TRY(enf_ldj_total(ldj_mol, d.B, eps ? w.log_q : nullptr, ldj, st));
+    return ENF_OK;
+}
+
+extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* params, float* grads, const float* h_in,
+                                    const float* box, const int* mol_off, const float* eps, void* workspace,
+                                    size_t workspace_bytes, float* dh, float* dg, float* dpos, float* dvel,
+                                    const float* dldj, int* status, void* stream) {
+    ENF_TRY(check_dims(dims));
+    const enflow_dims_t& d = *dims;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace w = carve(d, workspace, 1);
+    ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+    const int nf = d.nf;
+    for (int l = d.L - 1; l >= 0; --l) {
+        const LayerSave& sv = w.layer[l];
+        const float* lp = layer_params(params, nf, l);
+        float* lg = layer_params(grads, nf, l);
+        // coupling step (dynamics.py:14-21): gradients w.r.t. Q, F, G and the incoming state
+        ENF_TRY(enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
+        // node_model (egcl.py:65-69)
+        ENF_TRY(enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, w.dagg, dh, lg, w.partial, st));
+        // edge_model + force_model (egcl.py:57-63,71-75); P/S are recomputed, not stored
+        ENF_TRY(enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
+        ENF_TRY(enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
+                                   w.edges_ws, st));
+        ENF_TRY(enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf, w.wr, sv.z2,
+                             sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg, w.partial, st));
+        ENF_TRY(enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
+        ENF_TRY(enf_segment_sum128(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, st));
+        // coord_diff = pos[row] - pos[col] (data/base.py:17): +dd onto row atoms, -dd onto col atoms
+        ENF_TRY(enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
+        ENF_TRY(enf_segment_sum3(w.dd, w.colptr, w.perm, d.N, d.E_cap, 0, -1.0f, 1, dpos, st));
+        ENF_TRY(enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
+    }
+    if (eps)
+        ENF_TRY(enf_argmax_bwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), dh, dldj,
+                               argmax_params(grads, nf, d.L), w.partial, st));
+    (void)status;
+    return ENF_OK;
+}
+
+extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* params, float* h, float* g, float* pos,
+                                   float* vel, const float* box, const float* r_cut, const int* mol_off,
+                                   void* workspace, size_t workspace_bytes, int quantize, float* neg_ldj_mol,
+                                   int* status, void* stream) {
+    ENF_TRY(check_dims(dims));
+    const enflow_dims_t& d = *dims;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace w = carve(d, workspace, 0);
+    ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+    const int nf = d.nf;
+    if (neg_ldj_mol) cudaMemsetAsync(neg_ldj_mol, 0, sizeof(float) * d.B, st);
+    for (int l = 0; l < d.L; ++l)
+        ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
+    const LayerSave& sv = w.layer[0];
+    for (int l = d.L - 1; l >= 0; --l) {
+        ENF_TRY(enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
+        ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
+                             h, pos, box, r_cut, mol_off, status, st));                           // :31
+        ENF_TRY(enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
+    }
+    if (quantize) ENF_TRY(enf_argmax_reverse(h, d.N, nf, st));                                    // :35
+    return ENF_OK;
+}
+#pragma GCC visibility pop

@@ -1,0 +1,61 @@
+// Internal launch functions (one per kernel family); the extern "C" surface is in api.cu.
+#pragma once
+#include "common.cuh"
+
+int64_t enf_edges_workspace_ints(int N);
+template <typename T>
+int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int* mol_off, int B, int N, int E_cap,
+                      int* row, int* col, int* rowptr, int* ref_pos, int* E_dev, int* status, int* ws,
+                      cudaStream_t st);
+int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
+                       const int* E_dev, int* colptr, int* perm, int* ws, cudaStream_t st);
+
+int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
+                       cudaStream_t st);
+int enf_segment_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int mean, float scale,
+                     int accumulate, float* out, cudaStream_t st);
+
+int enf_pack_layer(const float* layer_params, int nf, float* packed, cudaStream_t st);
+int enf_node_pre_fwd(const float* h, int N, int nf, const float* lp, float* P, float* S, float* Q, cudaStream_t st);
+int64_t enf_node_pre_partial_floats(int N, int nf);
+int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float* dP, const float* dS,
+                     const float* dQ, float* dh, float* lgrad, float* partial, cudaStream_t st);
+int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* lp, const float* packed,
+                      float* z4, float* G, cudaStream_t st);
+int64_t enf_node_post_partial_floats(int N, int nf);
+int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const float* dG, int N, int nf,
+                      const float* lp, float* dagg, float* dh, float* lgrad, float* partial, cudaStream_t st);
+
+int64_t enf_edge_partial_floats();
+int enf_edge_fwd(const int* row, const int* col, const int* E_dev, int E_cap, const float* pos, const float* box,
+                 const float* P, const float* S, const float* lp, const float* packed, int nf, float* wr, float* z2,
+                 float* z3, float* s_out, float* trans, cudaStream_t st);
+int enf_edge_bwd(const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap, const float* pos,
+                 const float* box, const float* P, const float* S, const float* lp, int nf, float* wr,
+                 const float* z2, const float* z3, const float* s_saved, const float* dagg, const float* dF,
+                 float coords_weight, float* dz1, float* dd, float* lgrad, float* partial, cudaStream_t st);
+
+int enf_coupling_fwd(const float* Q, const float* F, const float* G, const float* h, const float* g,
+                     const float* pos, const float* vel, const float* box, const int* mol_off, int B, int nf,
+                     float dt, float* h_o, float* g_o, float* pos_o, float* vel_o, float* ldj_mol, cudaStream_t st);
+int enf_coupling_bwd(const float* Q, const float* vel_in, const float* dldj, int N, int nf, float dt, float* dh,
+                     float* dg, float* dpos, float* dvel, float* dQ, float* dF, float* dG, cudaStream_t st);
+int enf_coupling_inv_pre(const float* g, const float* vel, const float* box, int N, int nf, float dt, float* h,
+                         float* pos, cudaStream_t st);
+int enf_coupling_inv_post(const float* Q, const float* F, const float* G, const int* mol_off, int B, int nf,
+                          float dt, float* g, float* vel, float* neg_ldj_mol, cudaStream_t st);
+
+int enf_argmax_fwd(const float* h, const float* eps, int N, int nf, const float* ap, const int* mol_off, int B,
+                   float* z, float* logq_atom, double* logq_mol, float* log_q, cudaStream_t st);
+int64_t enf_argmax_partial_floats(int N, int nf);
+int enf_argmax_bwd(const float* h, const float* eps, int N, int nf, const float* ap, const float* dz,
+                   const float* dlogq, float* agrad, float* partial, cudaStream_t st);
+int enf_argmax_reverse(float* h, int N, int nf, cudaStream_t st);
+
+int enf_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B, int N,
+                int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj, double* mol_term,
+                float* loss, cudaStream_t st);
+int enf_nll_bwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B, int nf,
+                int max_n, float kBT, float softening, const float* dloss, float* dpos, float* dvel, float* dh,
+                float* dg, float* dldj, cudaStream_t st);
+int enf_ldj_total(const float* ldj_mol, int B, const float* log_q, float* ldj, cudaStream_t st);

@@ -1,0 +1,104 @@
+// K2: deterministic segmented reductions over row-sorted (CSR) edge data.
+// Replaces unsorted_segment_sum / unsorted_segment_mean (enflow/utils/helpers.py:54-70), whose
+// scatter_add_ is an unordered atomicAdd on CUDA.  Here every output row is owned by one warp that
+// walks its segment in edge order, so the sum order is fixed (run-to-run bit-identical).
+//
+// Bandwidth shape: each lane owns 4 consecutive features (one 16 B load per edge row, 512 B per
+// warp-wide request, fully coalesced); UNROLL independent loads are in flight per lane.
+// Algorithmic bytes per call: E*H*4 (messages) + (N+1)*4 (rowptr) + N*H*4 (output).
+#include "common.cuh"
+
+namespace {
+
+template <bool SILU, bool PERM>
+__global__ void __launch_bounds__(256) k_segment_sum128(const float* __restrict__ x, const int* __restrict__ ptr,
+                                                         const int* __restrict__ perm, int N, int E_cap,
+                                                         float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps_per_grid) {
+        int e0 = ptr[i], e1 = ptr[i + 1];
+        if (e1 > E_cap) e1 = E_cap;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = e0;
+        constexpr int UNROLL = 4;
+        for (; e + UNROLL <= e1; e += UNROLL) {
+            float4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int src = PERM ? perm[e + u] : (e + u);
+                v[u] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)src * ENF_H) + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (SILU) { v[u].x = siluf_(v[u].x); v[u].y = siluf_(v[u].y); v[u].z = siluf_(v[u].z); v[u].w = siluf_(v[u].w); }
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            }
+        }
+        for (; e < e1; ++e) {
+            const int src = PERM ? perm[e] : e;
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)src * ENF_H) + lane);
+            if (SILU) { v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w); }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out + (int64_t)i * ENF_H)[lane] = acc;
+    }
+}
+
+// 3-vector per edge (coordinate updates): lanes stride over the segment, then a fixed xor tree.
+// out[i] = scale * sum / (MEAN ? max(deg,1) : 1)   (helpers.py:70 count.clamp(min=1), quirk Q12)
+// With sign/accumulate options it also serves the backward scatter of d(coord_diff) onto positions.
+template <bool PERM>
+__global__ void __launch_bounds__(256) k_segment_sum3(const float* __restrict__ x, const int* __restrict__ ptr,
+                                                       const int* __restrict__ perm, int N, int E_cap, int mean,
+                                                       float scale, int accumulate, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps_per_grid) {
+        int e0 = ptr[i], e1 = ptr[i + 1];
+        if (e1 > E_cap) e1 = E_cap;
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int src = PERM ? perm[e] : e;
+            ax += x[(int64_t)src * 3 + 0];
+            ay += x[(int64_t)src * 3 + 1];
+            az += x[(int64_t)src * 3 + 2];
+        }
+        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+        if (lane < 3) {
+            float v = lane == 0 ? ax : (lane == 1 ? ay : az);
+            const int deg = e1 - e0;
+            if (mean) v = v / (float)(deg > 1 ? deg : 1);
+            v *= scale;
+            float* o = out + (int64_t)i * 3 + lane;
+            *o = accumulate ? (*o + v) : v;
+        }
+    }
+}
+
+}  // namespace
+
+int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
+                       cudaStream_t st) {
+    if (N == 0) return ENF_OK;
+    const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
+    if (perm) {
+        if (apply_silu) k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        else k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+    } else {
+        if (apply_silu) k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        else k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+    }
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
+int enf_segment_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int mean, float scale,
+                     int accumulate, float* out, cudaStream_t st) {
+    if (N == 0) return ENF_OK;
+    const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
+    if (perm) k_segment_sum3<true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, mean, scale, accumulate, out);
+    else k_segment_sum3<false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, mean, scale, accumulate, out);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}

@@ -1,0 +1,193 @@
+"""LFIntegrator with the reference's interface (`enflow/flow/dynamics.py:4-37`).
+
+``forward(data) -> (data, ldj)`` and ``reverse(data) -> data`` each make ONE call into the C library,
+which enqueues every kernel of the pass (neighbour lists, EGCLs, coupling steps, log-det) on the current
+stream.  ``ldj`` and the output state carry autograd: ``loss.backward()`` runs the hand-written backward
+pass through ``enflow_flow_backward`` and fills the flat gradient buffer.
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+from .base import BaseFlow
+
+
+def _prep(data):
+    """fp32 contiguous CUDA views of a Data batch + layout metadata."""
+    _lib.require_cuda(data.pos, data.h, data.g, data.vel, data.box)
+    B, off, max_n, n_cpu = data.meta()
+    dev = data.pos.device
+    return {
+        'h': _lib.f32c(data.h), 'g': _lib.f32c(data.g), 'pos': _lib.f32c(data.pos), 'vel': _lib.f32c(data.vel),
+        'box': _lib.f32c(data.box), 'r_cut': data.r_cut.detach().to(dev, torch.float32).reshape(-1).contiguous(),
+        'off': off, 'B': B, 'N': int(data.pos.shape[0]), 'max_n': max_n, 'n_cpu': n_cpu, 'dev': dev,
+    }
+
+
+class _FlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, b, eps, cap, training, h, g, pos, vel, *params):
+        L = _lib.lib()
+        dev = b['dev']
+        nf = flow.networks[0].input_nf
+        dims = _lib.Dims(b['B'], b['N'], nf, len(flow.networks), cap, b['max_n'], float(flow.dt),
+                         float(flow.networks[0].coords_weight))
+        nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), int(training))
+        ws = flow._take_workspace(nbytes, dev, training)
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        ho, go, po, vo = new(b['N'], nf), new(b['N'], nf), new(b['N'], 3), new(b['N'], 3)
+        ldj_mol, ldj = new(b['B']), new(1)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        p = _lib.ptr
+        _lib.check(L.enflow_flow_forward(ctypes.byref(dims), p(flow.flat_params), p(h), p(g), p(pos), p(vel),
+                                         p(b['box']), p(b['r_cut']), p(b['off']), p(eps), p(ws), nbytes,
+                                         int(training), p(ho), p(go), p(po), p(vo), p(ldj_mol), p(ldj), p(status),
+                                         _lib.stream()))
+        ctx.flow, ctx.b, ctx.eps, ctx.dims, ctx.ws, ctx.nbytes, ctx.h_in = flow, b, eps, dims, ws, nbytes, h
+        ctx.status = status
+        ctx.mark_non_differentiable(ldj_mol, status)
+        return ho, go, po, vo, ldj.reshape(()), ldj_mol, status
+
+    @staticmethod
+    def backward(ctx, dh, dg, dpos, dvel, dldj, _a, _b):
+        L = _lib.lib()
+        flow, b = ctx.flow, ctx.b
+        dev = b['dev']
+        nf = flow.networks[0].input_nf
+        z = lambda t, *s: (torch.zeros(*s, dtype=torch.float32, device=dev) if t is None
+                           else t.to(torch.float32).contiguous().clone())
+        dh, dg = z(dh, b['N'], nf), z(dg, b['N'], nf)
+        dpos, dvel = z(dpos, b['N'], 3), z(dvel, b['N'], 3)
+        dldj = z(dldj, 1).reshape(1)
+        params = flow._ordered_params()
+        aliased = any(q.grad is not None and q.grad.untyped_storage().data_ptr() ==
+                      flow.flat_grads.untyped_storage().data_ptr() for q in params)
+        grads = torch.zeros_like(flow.flat_grads) if aliased else flow.flat_grads.zero_()
+        p = _lib.ptr
+        _lib.check(L.enflow_flow_backward(ctypes.byref(ctx.dims), p(flow.flat_params), p(grads), p(ctx.h_in),
+                                          p(b['box']), p(b['off']), p(ctx.eps), p(ctx.ws), ctx.nbytes, p(dh), p(dg),
+                                          p(dpos), p(dvel), p(dldj), p(ctx.status), _lib.stream()))
+        flow._release_workspace(ctx.ws)
+        if flow._dp_group is not None:           # data parallel: one all-reduce over the flat buffer
+            import torch.distributed as dist
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=flow._dp_group)
+            grads.mul_(1.0 / dist.get_world_size(flow._dp_group))
+        views = flow.grad_views(grads)
+        return (None, None, None, None, None, dh, dg, dpos, dvel) + tuple(views)
+
+
+class LFIntegrator(BaseFlow):
+    def __init__(self, networks, dequant_network, dt):
+        super().__init__(networks, dequant_network, dt)
+        self._edge_caps = {}
+        self._ws_cache = None
+        self._ws_busy = False
+        self._dp_group = None
+        self.check_status = True
+        self.last_status = None
+
+    # ---- workspace: one cached buffer, a fresh one if a pending backward still owns the cached one
+    def _take_workspace(self, nbytes, dev, training):
+        ws = self._ws_cache
+        if ws is None or ws.numel() < nbytes or ws.device != dev or self._ws_busy:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            if not self._ws_busy:
+                self._ws_cache = ws
+        if training and ws is self._ws_cache:
+            self._ws_busy = True
+        return ws
+
+    def _release_workspace(self, ws):
+        if ws is self._ws_cache:
+            self._ws_busy = False
+
+    def make_networks(self, network):              # dynamics.py:5-8 (never called by Main, quirk Q14)
+        return [network for _ in range(getattr(self, 'n_iter', len(self.networks)))]
+
+    def _capacity(self, data, b):
+        n = b['n_cpu']
+        fc = int((n * (n - 1)).sum())
+        key = (b['B'], b['N'])
+        cap = self._edge_caps.get(key)
+        if cap is None:
+            e0 = int(data.build_edges(capacity=fc + 1024, reference_order=False).row.numel())
+            cap = e0 if e0 == fc else int(1.25 * e0) + 4096
+            cap = max(cap, 128)
+            self._edge_caps[key] = cap
+        return cap
+
+    def _run(self, data, eps, training):
+        b = _prep(data)
+        cap = self._capacity(data, b)
+        if eps is not None:
+            eps = _lib.f32c(eps.to(b['dev']))
+        while True:
+            out = _FlowFn.apply(self, b, eps, cap, training, b['h'], b['g'], b['pos'], b['vel'],
+                                *(self._ordered_params() if training else ()))
+            status = out[6]
+            self.last_status = status
+            if not self.check_status:
+                break
+            code = int(status.item())
+            if code & 2:
+                raise IndexError('neighbour list: fewer surviving image points than atoms '
+                                 '(the reference raises IndexError at enflow/data/base.py:137)')
+            if not (code & 1):
+                break
+            self._release_workspace(self._ws_cache)
+            cap *= 2
+            self._edge_caps[(b['B'], b['N'])] = cap
+        return out
+
+    def forward(self, data, eps=None):
+        """`dynamics.py:10-23`. ``eps`` (optional) injects the ArgMax noise; default ``torch.randn``."""
+        if eps is None:
+            eps = torch.randn(data.h.size(), device=data.h.device)          # argmax.py:17
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        h, g, pos, vel, ldj, ldj_mol, _ = self._run(data, eps, training)
+        data.h, data.g, data.pos, data.vel = h, g, pos, vel
+        data.ldj_mol = ldj_mol
+        return data, ldj
+
+    @torch.no_grad()
+    def reverse(self, data, quantize=True):
+        """`dynamics.py:25-37`; additionally leaves per-molecule -sum(Q) in ``data.neg_ldj_mol``."""
+        L = _lib.lib()
+        b = _prep(data)
+        cap = self._capacity(data, b)
+        dev = b['dev']
+        nf = self.networks[0].input_nf
+        h, g, pos, vel = (b[k].clone() for k in ('h', 'g', 'pos', 'vel'))
+        p = _lib.ptr
+        while True:
+            dims = _lib.Dims(b['B'], b['N'], nf, len(self.networks), cap, b['max_n'], float(self.dt),
+                             float(self.networks[0].coords_weight))
+            nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), 0)
+            ws = self._take_workspace(nbytes, dev, False)
+            neg = torch.empty(b['B'], dtype=torch.float32, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(L.enflow_flow_reverse(ctypes.byref(dims), p(self.flat_params), p(h), p(g), p(pos), p(vel),
+                                             p(b['box']), p(b['r_cut']), p(b['off']), p(ws), nbytes, int(quantize),
+                                             p(neg), p(status), _lib.stream()))
+            code = int(status.item()) if self.check_status else 0
+            if code & 2:
+                raise IndexError('neighbour list: fewer surviving image points than atoms')
+            if not (code & 1):
+                break
+            cap *= 2
+            self._edge_caps[(b['B'], b['N'])] = cap
+            h, g, pos, vel = (b[k].clone() for k in ('h', 'g', 'pos', 'vel'))
+        data.h, data.g, data.pos, data.vel = h, g, pos, vel
+        data.neg_ldj_mol = neg
+        return data
+
+
+class VVIntegrator(BaseFlow):
+    """`dynamics.py:39-86` is dead code upstream (forward raises TypeError, reverse calls a missing
+    method); there is nothing to be in parity with, so it is not provided."""
+
+    def forward(self, data):
+        raise NotImplementedError('VVIntegrator cannot run in the reference (enflow/flow/dynamics.py:46-48,85)')
+
+    reverse = forward

@@ -1,0 +1,135 @@
+/* enflow_b200 C ABI: the drop-in boundary of the B200 hot path.
+ *
+ * The reference (bharath-raghavan/enflow) is pure Python/PyTorch and has no FFI; these entry points
+ * are what a binding for its hot path would call.  Each one names the reference code it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; floats are fp32, indices int32;
+ *   - the caller owns all memory (inputs, outputs, workspace); the library never allocates or frees
+ *     device memory and keeps no reference after a call returns (calls are stream-ordered);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok; non-zero = failure, message from enflow_last_error() (thread-local);
+ *   - `status` (int[1], device) receives OR-ed flags: 1 = edge capacity exceeded (E > E_cap),
+ *     2 = the reference's id_mapping lookup would have raised IndexError (data/base.py:137);
+ *   - molecules are contiguous: molecule m owns atoms [mol_off[m], mol_off[m+1]).
+ *   - hidden width is fixed at 128 (example/train.yaml:19), node features nf <= 8.
+ */
+#ifndef ENFLOW_B200_H
+#define ENFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int32_t B;             /* molecules in the batch                                   */
+    int32_t N;             /* atoms in the batch                                       */
+    int32_t nf;            /* node features                                            */
+    int32_t L;             /* coupling steps = number of EGCLs (dynamics n_iter)       */
+    int32_t E_cap;         /* edge capacity per layer                                  */
+    int32_t max_n;         /* atoms in the largest molecule                            */
+    float dt;              /* leap-frog step in LJ time units                          */
+    float coords_weight;   /* EGCL coords_weight (egcl.py:11), 1.0 in Main             */
+} enflow_dims_t;
+
+const char* enflow_last_error(void);
+int enflow_version(void);
+int enflow_hidden(void);
+
+/* ---- flat parameter buffer -------------------------------------------------------------------
+ * All parameters of LFIntegrator(networks=L x EGCL, dequantize=ArgMax) live in ONE fp32 buffer
+ * (gradients in a second one with the same layout, so data-parallel training needs one all-reduce).
+ * enflow_param_layout writes, for the 15 EGCL tensors of every layer followed by the 4 ArgMax
+ * tensors, the offset (in floats) and element count, in state_dict order:
+ * networks.{i}.{edge_nn.0.weight, edge_nn.0.bias, edge_nn.2.weight, edge_nn.2.bias, node_nn.0.weight,
+ * node_nn.0.bias, node_nn.2.weight, node_nn.2.bias, coord_nn.0.weight, coord_nn.0.bias,
+ * coord_nn.2.weight, vel_scaling_nn.0.weight, .0.bias, .2.weight, .2.bias}, dequantize.network.{0,2}.{weight,bias}
+ * (enflow/nn/egcl.py:21-55, enflow/nn/argmax.py:9-12, enflow/flow/base.py:8-9).
+ * offsets/counts: host arrays of 15*L + 4 entries.  Returns the total buffer length in floats. */
+int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts);
+
+/* ---- K0 neighbour list: Data.edges (enflow/data/base.py:122-144, utils/helpers.py:15-29) -------
+ * pos/box are fp32 (pos_is_f64 = 0) or fp64 (1).  Output is grouped by row (CSR): row/col [E_cap],
+ * rowptr [N+1]; ref_pos[e] (nullable) is the index the edge has in the reference's own ordering.
+ * E_dev: int[2] = {min(E, E_cap), E}.  ws: int workspace of enflow_edges_workspace_ints(N). */
+int64_t enflow_edges_workspace_ints(int N);
+int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const float* r_cut, const int32_t* mol_off,
+                       int B, int N, int E_cap, int32_t* row, int32_t* col, int32_t* rowptr, int32_t* ref_pos,
+                       int32_t* E_dev, int32_t* status, int32_t* ws, void* stream);
+/* column-grouped view of the same edges (needed by the backward scatter onto `col`): colptr [N+1], perm [E_cap] */
+int enflow_build_col_perm(const int32_t* col, const int32_t* rowptr, const int32_t* mol_off, int B, int N, int E_cap,
+                          const int32_t* E_dev, int32_t* colptr, int32_t* perm, int32_t* ws, void* stream);
+
+/* ---- K2 segmented reductions: unsorted_segment_sum / _mean (enflow/utils/helpers.py:54-70) ------
+ * x [E,128] (or [E,3]) in CSR order, ptr [N+1]; perm (nullable) gathers rows x[perm[e]] instead.
+ * apply_silu: reduce silu(x).  mean: divide by max(deg,1).  accumulate: out += result. */
+int enflow_segment_sum128(const float* x, const int32_t* ptr, const int32_t* perm, int N, int E_cap, int apply_silu,
+                          float* out, void* stream);
+int enflow_segment_sum3(const float* x, const int32_t* ptr, const int32_t* perm, int N, int E_cap, int mean,
+                        float scale, int accumulate, float* out, void* stream);
+
+/* ---- EGCL pieces (enflow/nn/egcl.py:57-93); layer_params points at one layer inside the flat buffer */
+int64_t enflow_pack_floats(int nf);
+int enflow_pack_layer(const float* layer_params, int nf, float* packed, void* stream);
+int enflow_node_pre_fwd(const float* h, int N, int nf, const float* layer_params, float* P, float* S, float* Q,
+                        void* stream);
+int enflow_edge_fwd(const int32_t* row, const int32_t* col, const int32_t* E_dev, int E_cap, const float* pos,
+                    const float* box, const float* P, const float* S, const float* layer_params, const float* packed,
+                    int nf, float* wr_scratch, float* z2, float* z3, float* s, float* trans, void* stream);
+int enflow_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* layer_params,
+                         const float* packed, float* z4, float* G, void* stream);
+
+/* ---- K3 coupling: LFIntegrator.forward/reverse body (enflow/flow/dynamics.py:14-21, 27-33) ---- */
+int enflow_coupling_fwd(const float* Q, const float* F, const float* G, const float* h, const float* g,
+                        const float* pos, const float* vel, const float* box, const int32_t* mol_off, int B, int nf,
+                        float dt, float* h_out, float* g_out, float* pos_out, float* vel_out, float* ldj_mol,
+                        void* stream);
+int enflow_coupling_bwd(const float* Q, const float* vel_in, const float* dldj, int N, int nf, float dt, float* dh,
+                        float* dg, float* dpos, float* dvel, float* dQ, float* dF, float* dG, void* stream);
+int enflow_coupling_inv_pre(const float* g, const float* vel, const float* box, int N, int nf, float dt, float* h,
+                            float* pos, void* stream);
+int enflow_coupling_inv_post(const float* Q, const float* F, const float* G, const int32_t* mol_off, int B, int nf,
+                             float dt, float* g, float* vel, float* neg_ldj_mol, void* stream);
+
+/* ---- K4 dequantiser: ArgMax.forward (enflow/nn/argmax.py:14-26); eps is the injected N(0,1) noise */
+int enflow_argmax_fwd(const float* h, const float* eps, int N, int nf, const float* argmax_params,
+                      const int32_t* mol_off, int B, float* z, float* logq_atom, double* logq_mol, float* log_q,
+                      void* stream);
+
+/* ---- K5 likelihood: Alchemical_NLL (enflow/flow/loss.py:11-25) -------------------------------- */
+int enflow_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int32_t* mol_off, int B,
+                   int N, int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj,
+                   double* mol_term, float* loss, void* stream);
+int enflow_nll_bwd(const float* pos, const float* vel, const float* h, const float* g, const int32_t* mol_off, int B,
+                   int nf, int max_n, float kBT, float softening, const float* dloss, float* dpos, float* dvel,
+                   float* dh, float* dg, float* dldj, void* stream);
+
+/* ---- whole flow: LFIntegrator.forward / its backward / .reverse (enflow/flow/dynamics.py:10-37) --
+ * One call enqueues every kernel of the pass on `stream`; no host synchronisation inside.
+ * workspace: enflow_flow_workspace_bytes(dims, training) bytes, reused by the matching backward.
+ * eps: [N,nf] ArgMax noise, or NULL to skip dequantisation (h_in is then used as is).
+ * Outputs: state after L steps, ldj_mol [B] = per-molecule sum of Q, ldj [1] = log_q + sum ldj_mol. */
+size_t enflow_flow_workspace_bytes(const enflow_dims_t* dims, int training);
+int enflow_flow_forward(const enflow_dims_t* dims, const float* params, const float* h_in, const float* g_in,
+                        const float* pos_in, const float* vel_in, const float* box, const float* r_cut,
+                        const int32_t* mol_off, const float* eps, void* workspace, size_t workspace_bytes,
+                        int training, float* h_out, float* g_out, float* pos_out, float* vel_out, float* ldj_mol,
+                        float* ldj, int32_t* status, void* stream);
+/* d*_out: gradients w.r.t. the forward outputs (consumed/overwritten); dldj [1]; grads: flat buffer, accumulated (+=) */
+int enflow_flow_backward(const enflow_dims_t* dims, const float* params, float* grads, const float* h_in,
+                         const float* box, const int32_t* mol_off, const float* eps, void* workspace,
+                         size_t workspace_bytes, float* dh_out, float* dg_out, float* dpos_out, float* dvel_out,
+                         const float* dldj, int32_t* status, void* stream);
+/* in-place inverse; neg_ldj_mol [B] (nullable) receives -sum(Q) per molecule; quantize: apply ArgMax.reverse */
+int enflow_flow_reverse(const enflow_dims_t* dims, const float* params, float* h, float* g, float* pos, float* vel,
+                        const float* box, const float* r_cut, const int32_t* mol_off, void* workspace,
+                        size_t workspace_bytes, int quantize, float* neg_ldj_mol, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

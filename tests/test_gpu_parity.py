@@ -1,0 +1,232 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors + CPU oracle.
+
+Tolerances (BASELINE.json north star): fp32 mode log-likelihood and latents within 1e-5 relative,
+edge/index construction bit-exact.  Gradients are held to 1e-4 relative (L2, per tensor).
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, load_case
+from gpu_util import DEV, build_model, gpu_batch, rel_err, to_np
+from oracle import enflow_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def oracle_trace(c):
+    p = orc.params_to_torch(c['sd'])
+    b = orc.to_torch(c['batch'])
+    trace = []
+    with torch.no_grad():
+        state, ldj, ldj_mol = orc.lf_forward(p, c['L'], b, c['dt'], torch.as_tensor(c['eps']), trace=trace)
+        z0, log_q = orc.argmax_forward(p, b['h'], torch.as_tensor(c['eps']))
+    return trace, state, ldj, ldj_mol, z0, log_q
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_edges_bit_exact_vs_golden(name):
+    """K0 on the reference's own fp64 positions reproduces Data.edges exactly, in the reference order."""
+    c = load_case(name)
+    trace = oracle_trace(c)[0]
+    arrs = dict(c['batch'])
+    for i in range(c['L']):
+        if i > 0:
+            arrs['pos'] = trace[i - 1]['pos'].numpy()          # fp64 positions entering layer i
+        e = gpu_batch(arrs).edges
+        assert np.array_equal(e.row.cpu().numpy(), c['gold'][f'row{i}'].astype(np.int64)), f'layer {i} row'
+        assert np.array_equal(e.col.cpu().numpy(), c['gold'][f'col{i}'].astype(np.int64)), f'layer {i} col'
+        r32, c32, rowptr, e_dev = e.csr
+        assert bool((r32[1:] >= r32[:-1]).all()), 'CSR form must be row-grouped'
+        assert int(rowptr[-1]) == r32.numel()
+
+
+@pytest.mark.parametrize('name', ['c1_pbc', 'c5_small'])
+def test_edges_fp32_inputs_match_oracle(name):
+    """fp32 positions (the hot path's state) upcast exactly: same edges as the oracle on those values."""
+    c = load_case(name)
+    arrs = dict(c['batch'])
+    rs = np.random.RandomState(5)
+    arrs['pos'] = (arrs['pos'] + rs.normal(0, 0.05, arrs['pos'].shape)).astype(np.float32).astype(np.float64)
+    b = orc.to_torch(arrs)
+    row, col, _ = orc.build_edges(b['pos'], b['box'], b['N'], b['r_cut'])
+    e = gpu_batch(arrs, dtype=torch.float32).edges
+    assert np.array_equal(e.row.cpu().numpy(), row.numpy())
+    assert np.array_equal(e.col.cpu().numpy(), col.numpy())
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_egcl_layers_vs_golden(name):
+    """EGCL.forward(h, edges) per layer, fed the oracle's layer inputs: Q, F, G against the reference."""
+    c = load_case(name)
+    trace, _, _, _, z0, _ = oracle_trace(c)
+    model = build_model(c['sd'], c['nf'], c['L'])
+    arrs = dict(c['batch'])
+    h = z0.numpy()
+    for i in range(c['L']):
+        if i > 0:
+            arrs['pos'], h = trace[i - 1]['pos'].numpy(), trace[i - 1]['h'].numpy()
+        data = gpu_batch(arrs)
+        Q, F, G = model.networks[i](torch.as_tensor(h, device=DEV), data.edges)
+        for k, v in (('Q', Q), ('F', F), ('G', G)):
+            err = rel_err(to_np(v), c['gold'][f'{k}{i}'])
+            assert err < FWD_TOL, f'layer {i} {k}: rel err {err:.3e}'
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_flow_forward_and_loss_vs_golden(name):
+    from enflow_b200.flow.loss import Alchemical_NLL
+    c = load_case(name)
+    model = build_model(c['sd'], c['nf'], c['L'])
+    data = gpu_batch(c['batch'])
+    with torch.no_grad():
+        out, ldj = model(data, eps=torch.as_tensor(c['eps']))
+        loss = Alchemical_NLL(kBT=c['kBT'], softening=c['softening'])(out, ldj)
+    for k in ('h', 'g', 'pos', 'vel'):
+        err = rel_err(to_np(getattr(out, k)), c['gold'][f'out_{k}'])
+        assert err < FWD_TOL, f'{k}: rel err {err:.3e}'
+    assert abs(ldj.item() - float(c['gold']['ldj'])) <= FWD_TOL * max(abs(float(c['gold']['ldj'])), 1.0) * 4
+    assert abs(loss.item() - float(c['gold']['loss'])) <= FWD_TOL * abs(float(c['gold']['loss']))
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_flow_backward_vs_oracle(name):
+    from enflow_b200.flow.loss import Alchemical_NLL
+    c = load_case(name)
+    model = build_model(c['sd'], c['nf'], c['L'])
+    data = gpu_batch(c['batch'])
+    out, ldj = model(data, eps=torch.as_tensor(c['eps']))
+    loss = Alchemical_NLL(kBT=c['kBT'], softening=c['softening'])(out, ldj)
+    loss.backward()
+    ref_loss, ref_grads, _, _, _ = orc.train_step(c['sd'], c['L'], c['batch'], c['dt'], c['eps'], c['kBT'], c['softening'])
+    assert abs(loss.item() - ref_loss.item()) <= FWD_TOL * abs(ref_loss.item())
+    worst = []
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        g, r = to_np(p.grad), ref_grads[k].numpy()
+        err = np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-300)
+        worst.append((err, k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < GRAD_TOL, f'worst gradient errors: {worst[:5]}'
+
+
+@pytest.mark.parametrize('name', ['c1_pbc', 'c2_ragged', 'c3_lj55'])
+def test_reverse_vs_golden(name):
+    c = load_case(name)
+    model = build_model(c['sd'], c['nf'], c['L'])
+    arrs = dict(c['batch'])
+    for k in ('h', 'g', 'pos', 'vel'):
+        arrs[k] = c['gold'][f'out_{k}']
+    back = model.reverse(gpu_batch(arrs))
+    for k in ('g', 'pos', 'vel'):
+        err = rel_err(to_np(getattr(back, k)), c['gold'][f'rev_{k}'])
+        assert err < 2e-5, f'{k}: rel err {err:.3e}'
+    assert np.array_equal(to_np(back.h), c['gold']['rev_h'])          # one-hot after ArgMax.reverse
+
+
+def test_round_trip_and_neg_ldj():
+    """reverse(forward(x)) == x (the reference's own self-check, enflow/main.py:275-278) and
+    the per-molecule -sum(Q) of the inverse equals minus the forward's per-molecule log-det."""
+    c = load_case('c2_ragged')
+    model = build_model(c['sd'], c['nf'], c['L'])
+    data = gpu_batch(c['batch'])
+    with torch.no_grad():
+        out, ldj = model(data, eps=torch.as_tensor(c['eps']))
+    fwd_ldj_mol = out.ldj_mol.clone()
+    z_after_dequant = None
+    back = model.reverse(out, quantize=True)
+    assert rel_err(to_np(back.pos), c['batch']['pos']) < 1e-5
+    assert rel_err(to_np(back.vel), c['batch']['vel']) < 1e-5
+    assert rel_err(to_np(back.g), c['batch']['g']) < 1e-5
+    assert np.array_equal(to_np(back.h), c['batch']['h'])
+    assert rel_err(to_np(back.neg_ldj_mol), -to_np(fwd_ldj_mol)) < 1e-5
+
+
+def test_deterministic_bitwise():
+    from enflow_b200.flow.loss import Alchemical_NLL
+    c = load_case('c1_pbc')
+    runs = []
+    for _ in range(2):
+        model = build_model(c['sd'], c['nf'], c['L'])
+        out, ldj = model(gpu_batch(c['batch']), eps=torch.as_tensor(c['eps']))
+        loss = Alchemical_NLL(kBT=c['kBT'], softening=c['softening'])(out, ldj)
+        loss.backward()
+        runs.append((loss.detach().clone(), out.pos.detach().clone(), model.flat_grads.clone()))
+    assert torch.equal(runs[0][0], runs[1][0])
+    assert torch.equal(runs[0][1], runs[1][1])
+    assert torch.equal(runs[0][2], runs[1][2]), 'gradients must be bit-identical run to run'
+
+
+def _random_rotation(rs):
+    q, r = np.linalg.qr(rs.normal(size=(3, 3)))
+    q = q * np.sign(np.diag(r))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+def test_equivariance_fc_regime():
+    """Rotation / translation / per-molecule permutation in the well-defined (no-PBC) regime, SURVEY Q6."""
+    from enflow_b200.data import synthetic as syn
+    nf, L = 5, 3
+    arrs = syn.make_batch('c2', 5, ragged=True, seed=77)
+    sd = syn.make_weights(nf, 128, L, seed=3, coord_gain=0.5)
+    eps = syn.make_noise(int(arrs['N'].sum()), nf, seed=5)
+    model = build_model(sd, nf, L)
+
+    def run(a, e):
+        with torch.no_grad():
+            out, ldj = model(gpu_batch(a), eps=torch.as_tensor(e))
+        return {k: to_np(getattr(out, k)) for k in ('h', 'g', 'pos', 'vel')}, ldj.item(), to_np(out.ldj_mol)
+
+    base, ldj0, ldjm0 = run(arrs, eps)
+    rs = np.random.RandomState(11)
+    R = _random_rotation(rs)
+    rot = dict(arrs)
+    rot['pos'], rot['vel'] = arrs['pos'] @ R.T, arrs['vel'] @ R.T
+    o, ldj, _ = run(rot, eps)
+    assert abs(ldj - ldj0) < 1e-4 * max(abs(ldj0), 1)
+    assert rel_err(o['pos'], base['pos'] @ R.T) < 2e-5 and rel_err(o['vel'], base['vel'] @ R.T) < 2e-5
+    assert rel_err(o['h'], base['h']) < 2e-5 and rel_err(o['g'], base['g']) < 2e-5
+    tr = dict(arrs)
+    tr['pos'] = arrs['pos'] + np.array([0.3, -0.2, 0.1])
+    o, ldj, _ = run(tr, eps)
+    assert abs(ldj - ldj0) < 1e-4 * max(abs(ldj0), 1)
+    assert rel_err(o['pos'] - np.array([0.3, -0.2, 0.1]), base['pos']) < 2e-5
+    # permute atoms inside every molecule
+    perm, o0 = [], 0
+    for n in arrs['N']:
+        perm.append(o0 + rs.permutation(int(n)))
+        o0 += int(n)
+    perm = np.concatenate(perm)
+    pm = {k: (v[perm] if k in ('h', 'g', 'pos', 'vel', 'box') else v) for k, v in arrs.items()}
+    o, ldj, ldjm = run(pm, eps[perm])
+    assert abs(ldj - ldj0) < 1e-4 * max(abs(ldj0), 1)
+    assert rel_err(ldjm, ldjm0) < 1e-4
+    for k in ('h', 'g', 'pos', 'vel'):
+        assert rel_err(o[k], base[k][perm]) < 2e-5, k
+
+
+def test_edge_cases_single_atom_and_tiny_molecules():
+    """Molecules with 1 atom (no edges, mean count clamps to 1: Q12) next to 2- and 3-atom ones."""
+    from enflow_b200.data import synthetic as syn
+    from enflow_b200.flow.loss import Alchemical_NLL
+    nf, L = 5, 2
+    parts = [syn.make_batch('c2', 1, n_atoms=n, seed=100 + n) for n in (1, 2, 3, 1, 7)]
+    arrs = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    sd = syn.make_weights(nf, 128, L, seed=4, coord_gain=0.5)
+    eps = syn.make_noise(int(arrs['N'].sum()), nf, seed=6)
+    model = build_model(sd, nf, L)
+    out, ldj = model(gpu_batch(arrs), eps=torch.as_tensor(eps))
+    loss = Alchemical_NLL(kBT=syn.TRAIN_KBT, softening=0.1)(out, ldj)
+    loss.backward()
+    ref_loss, ref_grads, ref_state, _, _ = orc.train_step(sd, L, arrs, syn.TRAIN_DT, eps, syn.TRAIN_KBT, 0.1)
+    assert abs(loss.item() - ref_loss.item()) <= FWD_TOL * abs(ref_loss.item())
+    for k in ('h', 'g', 'pos', 'vel'):
+        assert rel_err(to_np(getattr(out, k)), ref_state[k].numpy()) < FWD_TOL, k
+    for k, p in model.named_parameters():
+        r = ref_grads[k].numpy()
+        assert np.linalg.norm(to_np(p.grad) - r) <= GRAD_TOL * max(np.linalg.norm(r), 1e-12), k
