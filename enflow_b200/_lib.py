@@ -26,6 +26,10 @@ SIGNATURES = {
     'enflow_last_error': (C.c_char_p, []),
     'enflow_version': (i32, []),
     'enflow_hidden': (i32, []),
+    'enflow_launch_count': (C.c_longlong, [i32]),
+    'enflow_timing_enable': (i32, [i32]),
+    'enflow_timing_kinds': (i32, []),
+    'enflow_timing_read': (i32, [C.POINTER(f32), C.POINTER(i32)]),
     'enflow_param_layout': (i64, [i32, i32, C.POINTER(i64), C.POINTER(i64)]),
     'enflow_edges_workspace_ints': (i64, [i32]),
     'enflow_build_edges': (i32, [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -101,3 +105,16 @@ def param_layout(nf, L):
     if total < 0:
         raise RuntimeError('enflow_b200: ' + lib().enflow_last_error().decode())
     return int(total), list(offs), list(cnts)
+
+
+TIMING_KINDS = ['edges', 'node_pre', 'edge_fwd', 'segment_sum128', 'segment_sum3', 'node_post', 'coupling',
+                'edge_bwd', 'node_bwd', 'col_perm', 'argmax', 'nll']
+
+
+def timing_read():
+    """{family: (total_ms, groups)} collected since enflow_timing_enable(1)."""
+    n = lib().enflow_timing_kinds()
+    ms = (f32 * n)()
+    cnt = (i32 * n)()
+    check(lib().enflow_timing_read(ms, cnt))
+    return {TIMING_KINDS[k]: (float(ms[k]), int(cnt[k])) for k in range(n)}

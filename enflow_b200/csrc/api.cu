@@ -15,12 +15,68 @@ void enf_set_error(const char* fmt, ...) {
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+// ---- instrumentation: launch counter and optional CUDA-event timing per kernel family ------------
+#include <vector>
+static long long g_launches = 0;
+void enf_count_launch() { ++g_launches; }
+
+struct TimingSlot { cudaEvent_t a, b; int kind; };
+static std::vector<TimingSlot> g_slots;
+static size_t g_used = 0;
+static bool g_timing = false;
+
+void enf_time_begin(int kind, cudaStream_t st) {
+    if (!g_timing) return;
+    if (g_used == g_slots.size()) {
+        TimingSlot s;
+        cudaEventCreate(&s.a);
+        cudaEventCreate(&s.b);
+        g_slots.push_back(s);
+    }
+    g_slots[g_used].kind = kind;
+    cudaEventRecord(g_slots[g_used].a, st);
+}
+void enf_time_end(cudaStream_t st) {
+    if (!g_timing) return;
+    cudaEventRecord(g_slots[g_used].b, st);
+    ++g_used;
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
 const char* enflow_last_error(void) { return g_err; }
 int enflow_version(void) { return 100; }
 int enflow_hidden(void) { return ENF_H; }
+
+long long enflow_launch_count(int reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+// enable != 0: start collecting (drops earlier samples); enable == 0: stop
+int enflow_timing_enable(int enable) {
+    g_timing = enable != 0;
+    if (enable) g_used = 0;
+    return ENF_OK;
+}
+// host arrays of enflow_timing_kinds() entries: summed milliseconds and launch-group counts per family.
+// Synchronises on the recorded events.
+int enflow_timing_kinds(void) { return TK_COUNT; }
+int enflow_timing_read(float* ms, int* counts) {
+    for (int k = 0; k < TK_COUNT; ++k) { ms[k] = 0.f; counts[k] = 0; }
+    for (size_t i = 0; i < g_used; ++i) {
+        float t = 0.f;
+        if (cudaEventSynchronize(g_slots[i].b) != cudaSuccess || cudaEventElapsedTime(&t, g_slots[i].a, g_slots[i].b) != cudaSuccess) {
+            enf_set_error("timing_read: event query failed");
+            return ENF_ERR_CUDA;
+        }
+        ms[g_slots[i].kind] += t;
+        counts[g_slots[i].kind] += 1;
+    }
+    g_used = 0;
+    return ENF_OK;
+}
 
 int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts) {
     if (nf < 1 || nf > ENF_MAX_NF || L < 1 || L > 16) { enf_set_error("param_layout: bad nf=%d or L=%d", nf, L); return -1; }
@@ -114,12 +170,18 @@ int enflow_argmax_fwd(const float* h, const float* eps, int N, int nf, const flo
 int enflow_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B,
                    int N, int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj,
                    double* mol_term, float* loss, void* stream) {
-    return enf_nll_fwd(pos, vel, h, g, mol_off, B, N, nf, max_n, kBT, softening, z_lj, ldj, mol_term, loss, ST(stream));
+    enf_time_begin(TK_NLL, ST(stream));
+    const int rc = enf_nll_fwd(pos, vel, h, g, mol_off, B, N, nf, max_n, kBT, softening, z_lj, ldj, mol_term, loss, ST(stream));
+    enf_time_end(ST(stream));
+    return rc;
 }
 int enflow_nll_bwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B,
                    int nf, int max_n, float kBT, float softening, const float* dloss, float* dpos, float* dvel,
                    float* dh, float* dg, float* dldj, void* stream) {
-    return enf_nll_bwd(pos, vel, h, g, mol_off, B, nf, max_n, kBT, softening, dloss, dpos, dvel, dh, dg, dldj, ST(stream));
+    enf_time_begin(TK_NLL, ST(stream));
+    const int rc = enf_nll_bwd(pos, vel, h, g, mol_off, B, nf, max_n, kBT, softening, dloss, dpos, dvel, dh, dg, dldj, ST(stream));
+    enf_time_end(ST(stream));
+    return rc;
 }
 
 }  // extern "C"

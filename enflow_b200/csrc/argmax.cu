@@ -237,7 +237,7 @@ int enf_argmax_reverse(float* h, int N, int nf, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     int blocks = (N + 255) / 256;
     if (blocks > enf_num_sms() * 8) blocks = enf_num_sms() * 8;
-    k_argmax_reverse<<<blocks, 256, 0, st>>>(h, N, nf);
+    enf_count_launch(), k_argmax_reverse<<<blocks, 256, 0, st>>>(h, N, nf);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -252,12 +252,12 @@ int enf_argmax_fwd(const float* h, const float* eps, int N, int nf, const float*
                    float* z, float* logq_atom, double* logq_mol, float* log_q, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const ArgmaxOffsets o = enf_argmax_offsets(nf);
-    k_argmax_fwd<<<tile_grid(N), TPB, 0, st>>>(h, eps, N, nf, ap + o.off[PA_W0], ap + o.off[PA_B0], ap + o.off[PA_W2],
+    enf_count_launch(), k_argmax_fwd<<<tile_grid(N), TPB, 0, st>>>(h, eps, N, nf, ap + o.off[PA_W0], ap + o.off[PA_B0], ap + o.off[PA_W2],
                                                ap + o.off[PA_B2], z, logq_atom);
     int mg = (B + 7) / 8;
     if (mg > enf_num_sms() * 8) mg = enf_num_sms() * 8;
-    k_mol_sum<<<mg, 256, 0, st>>>(logq_atom, mol_off, B, logq_mol);
-    k_total<<<1, 256, 0, st>>>(logq_mol, B, -0.5 * 1.8378770664093453 /* log(2 pi) */, log_q);
+    enf_count_launch(), k_mol_sum<<<mg, 256, 0, st>>>(logq_atom, mol_off, B, logq_mol);
+    enf_count_launch(), k_total<<<1, 256, 0, st>>>(logq_mol, B, -0.5 * 1.8378770664093453 /* log(2 pi) */, log_q);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -271,10 +271,10 @@ int enf_argmax_bwd(const float* h, const float* eps, int N, int nf, const float*
     if (N == 0) return ENF_OK;
     const ArgmaxOffsets o = enf_argmax_offsets(nf);
     const int grid = tile_grid(N);
-    k_argmax_bwd<<<grid, TPB, 0, st>>>(h, eps, N, nf, ap + o.off[PA_W0], ap + o.off[PA_B0], ap + o.off[PA_W2],
+    enf_count_launch(), k_argmax_bwd<<<grid, TPB, 0, st>>>(h, eps, N, nf, ap + o.off[PA_W0], ap + o.off[PA_B0], ap + o.off[PA_W2],
                                        ap + o.off[PA_B2], dz, dlogq, partial);
     const int stride = ENF_H * nf + ENF_H + 2 * nf * ENF_H + 2 * nf;
-    k_argmax_reduce<<<(stride + 255) / 256, 256, 0, st>>>(partial, grid, stride, nf, (int)o.off[PA_W0],
+    enf_count_launch(), k_argmax_reduce<<<(stride + 255) / 256, 256, 0, st>>>(partial, grid, stride, nf, (int)o.off[PA_W0],
                                                            (int)o.off[PA_B0], (int)o.off[PA_W2], (int)o.off[PA_B2], agrad);
     ENF_CHECK_LAUNCH();
     return ENF_OK;

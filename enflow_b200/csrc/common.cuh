@@ -14,6 +14,12 @@
 #define ENF_ERR_CUDA 2
 
 void enf_set_error(const char* fmt, ...);
+void enf_count_launch();                                  // every kernel launch of this library is counted
+// optional per-kernel-family timing with CUDA events on the launch stream (see enflow_timing_*)
+enum { TK_EDGES = 0, TK_NODE_PRE, TK_EDGE_FWD, TK_SEG128, TK_SEG3, TK_NODE_POST, TK_COUPLING, TK_EDGE_BWD,
+       TK_NODE_BWD, TK_COL_PERM, TK_ARGMAX, TK_NLL, TK_COUNT };
+void enf_time_begin(int kind, cudaStream_t st);
+void enf_time_end(cudaStream_t st);
 
 #define ENF_CHECK_ARG(cond, ...)                 \
     do {                                         \

@@ -125,7 +125,7 @@ int enf_coupling_fwd(const float* Q, const float* F, const float* G, const float
                      const float* pos, const float* vel, const float* box, const int* mol_off, int B, int nf,
                      float dt, float* h_o, float* g_o, float* pos_o, float* vel_o, float* ldj_mol, cudaStream_t st) {
     if (B == 0) return ENF_OK;
-    k_coupling_fwd<<<mol_grid(B), 256, 0, st>>>(Q, F, G, h, g, pos, vel, box, mol_off, B, nf, dt, h_o, g_o, pos_o,
+    enf_count_launch(), k_coupling_fwd<<<mol_grid(B), 256, 0, st>>>(Q, F, G, h, g, pos, vel, box, mol_off, B, nf, dt, h_o, g_o, pos_o,
                                                  vel_o, ldj_mol);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
@@ -134,7 +134,7 @@ int enf_coupling_fwd(const float* Q, const float* F, const float* G, const float
 int enf_coupling_bwd(const float* Q, const float* vel_in, const float* dldj, int N, int nf, float dt, float* dh,
                      float* dg, float* dpos, float* dvel, float* dQ, float* dF, float* dG, cudaStream_t st) {
     if (N == 0) return ENF_OK;
-    k_coupling_bwd<<<atom_grid(N), 256, 0, st>>>(Q, vel_in, dldj, N, nf, dt, dh, dg, dpos, dvel, dQ, dF, dG);
+    enf_count_launch(), k_coupling_bwd<<<atom_grid(N), 256, 0, st>>>(Q, vel_in, dldj, N, nf, dt, dh, dg, dpos, dvel, dQ, dF, dG);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -142,7 +142,7 @@ int enf_coupling_bwd(const float* Q, const float* vel_in, const float* dldj, int
 int enf_coupling_inv_pre(const float* g, const float* vel, const float* box, int N, int nf, float dt, float* h,
                          float* pos, cudaStream_t st) {
     if (N == 0) return ENF_OK;
-    k_coupling_inv_pre<<<atom_grid(N), 256, 0, st>>>(g, vel, box, N, nf, dt, h, pos);
+    enf_count_launch(), k_coupling_inv_pre<<<atom_grid(N), 256, 0, st>>>(g, vel, box, N, nf, dt, h, pos);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -150,7 +150,7 @@ int enf_coupling_inv_pre(const float* g, const float* vel, const float* box, int
 int enf_coupling_inv_post(const float* Q, const float* F, const float* G, const int* mol_off, int B, int nf,
                           float dt, float* g, float* vel, float* neg_ldj_mol, cudaStream_t st) {
     if (B == 0) return ENF_OK;
-    k_coupling_inv_post<<<mol_grid(B), 256, 0, st>>>(Q, F, G, mol_off, B, nf, dt, g, vel, neg_ldj_mol);
+    enf_count_launch(), k_coupling_inv_post<<<mol_grid(B), 256, 0, st>>>(Q, F, G, mol_off, B, nf, dt, g, vel, neg_ldj_mol);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

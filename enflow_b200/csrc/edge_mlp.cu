@@ -501,10 +501,10 @@ int enf_edge_fwd(const int* row, const int* col, const int* E_dev, int E_cap, co
         cudaFuncSetAttribute(k_edge_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem());
         attr = true;
     }
-    k_extract_wr<<<1, ENF_H, 0, st>>>(lp + o.off[P_W1], 2 * nf + 1, wr);
+    enf_count_launch(), k_extract_wr<<<1, ENF_H, 0, st>>>(lp + o.off[P_W1], 2 * nf + 1, wr);
     int grid = (E_cap + TE - 1) / TE;
     if (grid > enf_edge_fwd_grid()) grid = enf_edge_fwd_grid();
-    k_edge_fwd<<<grid, THREADS, fwd_smem(), st>>>(row, col, E_dev, pos, box, P, S, wr, packed + p.w2t,
+    enf_count_launch(), k_edge_fwd<<<grid, THREADS, fwd_smem(), st>>>(row, col, E_dev, pos, box, P, S, wr, packed + p.w2t,
                                                   lp + o.off[P_B2], packed + p.w3t, lp + o.off[P_B3],
                                                   lp + o.off[P_WC], z2, z3, s_out, trans);
     ENF_CHECK_LAUNCH();
@@ -524,11 +524,11 @@ int enf_edge_bwd(const int* row, const int* col, const int* rowptr, const int* E
     }
     const int grid = enf_edge_bwd_grid();
     cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * EDGE_PARTIAL, st);
-    k_extract_wr<<<1, ENF_H, 0, st>>>(lp + o.off[P_W1], 2 * nf + 1, wr);
-    k_edge_bwd<<<grid, THREADS, bwd_smem(), st>>>(row, col, rowptr, E_dev, pos, box, P, S, wr, lp + o.off[P_W2],
+    enf_count_launch(), k_extract_wr<<<1, ENF_H, 0, st>>>(lp + o.off[P_W1], 2 * nf + 1, wr);
+    enf_count_launch(), k_edge_bwd<<<grid, THREADS, bwd_smem(), st>>>(row, col, rowptr, E_dev, pos, box, P, S, wr, lp + o.off[P_W2],
                                                   lp + o.off[P_W3], lp + o.off[P_WC], z2, z3, s_saved, dagg, dF,
                                                   coords_weight, dz1, dd, partial);
-    k_edge_reduce<<<(EDGE_PARTIAL + 255) / 256, 256, 0, st>>>(partial, grid, (int)o.off[P_W2], (int)o.off[P_W3],
+    enf_count_launch(), k_edge_reduce<<<(EDGE_PARTIAL + 255) / 256, 256, 0, st>>>(partial, grid, (int)o.off[P_W2], (int)o.off[P_W3],
                                                               (int)o.off[P_B2], (int)o.off[P_B3], (int)o.off[P_WC],
                                                               (int)o.off[P_W1], 2 * nf + 1, lgrad);
     ENF_CHECK_LAUNCH();

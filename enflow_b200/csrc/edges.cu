@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, c
 static int scan2(int* a0, int* a1, int64_t n, int* sums, cudaStream_t st) {
     const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     dim3 g(nb, 2);
-    k_scan_sums<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
-    k_scan_top<<<dim3(1, 2), SCAN_THREADS, 0, st>>>(sums, nb);
-    k_scan_apply<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
+    enf_count_launch(), k_scan_sums<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
+    enf_count_launch(), k_scan_top<<<dim3(1, 2), SCAN_THREADS, 0, st>>>(sums, nb);
+    enf_count_launch(), k_scan_apply<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -286,17 +286,17 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     int* nsurv = cnt_ref + n27 + 1;
     int* atom_mol = nsurv + N;
     int* sums = atom_mol + N + (2 * N + 1);   // colcnt/cursor live between (see enf_build_col_perm)
-    k_atom_mol<<<B, 128, 0, st>>>(mol_off, B, atom_mol);
-    k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv);
+    enf_count_launch(), k_atom_mol<<<B, 128, 0, st>>>(mol_off, B, atom_mol);
+    enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv);
     const int64_t warps = n27;
     const int blocks = (int)((warps * 32 + 255) / 256);
-    k_edges_hits<T, false><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
+    enf_count_launch(), k_edges_hits<T, false><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
                                                    cnt_ref, nullptr, nullptr, nullptr, nullptr, E_cap, status);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
-    k_edges_hits<T, true><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
+    enf_count_launch(), k_edges_hits<T, true><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
                                                   cnt_ref, row, col, ref_pos, rowptr, E_cap, status);
-    k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
+    enf_count_launch(), k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -316,11 +316,11 @@ int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, in
     int* sums = dummy + N + 1;
     cudaMemsetAsync(colptr, 0, sizeof(int) * (N + 1), st);
     cudaMemsetAsync(cursor, 0, sizeof(int) * (2LL * N + 1), st);
-    k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr);
+    enf_count_launch(), k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(colptr, dummy, N, sums, st));
     cudaMemsetAsync(cursor, 0, sizeof(int) * N, st);
-    k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap);
+    enf_count_launch(), k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

@@ -9,6 +9,13 @@ struct enflow_dims_t {
     float dt, coords_weight;
 };
 
+#define TIMED(kind, call)        \
+    do {                         \
+        enf_time_begin(kind, st); \
+        ENF_TRY(call);           \
+        enf_time_end(st);        \
+    } while (0)
+
 namespace {
 
 struct Bump {
@@ -111,14 +118,14 @@ void copy_f(float* dst, const float* src, size_t n, cudaStream_t st) {
 int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv, const float* lp, const float* packed,
                  const float* h, const float* pos, const float* box, const float* r_cut, const int* mol_off,
                  int* status, cudaStream_t st) {
-    ENF_TRY(enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
+    TIMED(TK_EDGES, enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
                                      sv.E_dev, status, w.edges_ws, st));
-    ENF_TRY(enf_node_pre_fwd(h, d.N, d.nf, lp, w.P, w.S, sv.Q, st));
-    ENF_TRY(enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr, sv.z2, sv.z3,
+    TIMED(TK_NODE_PRE, enf_node_pre_fwd(h, d.N, d.nf, lp, w.P, w.S, sv.Q, st));
+    TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr, sv.z2, sv.z3,
                          sv.s, w.trans, st));
-    ENF_TRY(enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
-    ENF_TRY(enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
-    ENF_TRY(enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
+    TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
+    TIMED(TK_SEG3, enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
+    TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
     return ENF_OK;
 }
 
@@ -147,7 +154,7 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
         ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
     // state entering layer 0: dequantised h (dynamics.py:11), everything else copied
     if (eps) {
-        ENF_TRY(enf_argmax_fwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), mol_off, d.B, w.h[0], w.logq_atom,
+        TIMED(TK_ARGMAX, enf_argmax_fwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), mol_off, d.B, w.h[0], w.logq_atom,
                                w.logq_mol, w.log_q, st));
     } else {
         copy_f(w.h[0], h_in, N * nf, st);
@@ -166,7 +173,7 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
         const LayerSave& sv = w.layer[training ? l : 0];
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
                              w.h[cur], w.pos[cur], box, r_cut, mol_off, status, st));
-        ENF_TRY(enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
+        TIMED(TK_COUPLING, enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
                                  ho, go, po, vo, ldj_mol, st));
     }
     ENF_TRY(enf_ldj_total(ldj_mol, d.B, eps ? w.log_q : nullptr, ldj, st));
@@ -188,24 +195,24 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         const float* lp = layer_params(params, nf, l);
         float* lg = layer_params(grads, nf, l);
         // coupling step (dynamics.py:14-21): gradients w.r.t. Q, F, G and the incoming state
-        ENF_TRY(enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
+        TIMED(TK_COUPLING, enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
         // node_model (egcl.py:65-69)
-        ENF_TRY(enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, w.dagg, dh, lg, w.partial, st));
+        TIMED(TK_NODE_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, w.dagg, dh, lg, w.partial, st));
         // edge_model + force_model (egcl.py:57-63,71-75); P/S are recomputed, not stored
-        ENF_TRY(enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
-        ENF_TRY(enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
+        TIMED(TK_NODE_PRE, enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
+        TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
                                    w.edges_ws, st));
-        ENF_TRY(enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf, w.wr, sv.z2,
+        TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf, w.wr, sv.z2,
                              sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg, w.partial, st));
-        ENF_TRY(enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
-        ENF_TRY(enf_segment_sum128(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, st));
+        TIMED(TK_SEG128, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
+        TIMED(TK_SEG128, enf_segment_sum128(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, st));
         // coord_diff = pos[row] - pos[col] (data/base.py:17): +dd onto row atoms, -dd onto col atoms
-        ENF_TRY(enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
-        ENF_TRY(enf_segment_sum3(w.dd, w.colptr, w.perm, d.N, d.E_cap, 0, -1.0f, 1, dpos, st));
-        ENF_TRY(enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
+        TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
+        TIMED(TK_SEG3, enf_segment_sum3(w.dd, w.colptr, w.perm, d.N, d.E_cap, 0, -1.0f, 1, dpos, st));
+        TIMED(TK_NODE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
     }
     if (eps)
-        ENF_TRY(enf_argmax_bwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), dh, dldj,
+        TIMED(TK_ARGMAX, enf_argmax_bwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), dh, dldj,
                                argmax_params(grads, nf, d.L), w.partial, st));
     (void)status;
     return ENF_OK;
@@ -226,10 +233,10 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
         ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
     const LayerSave& sv = w.layer[0];
     for (int l = d.L - 1; l >= 0; --l) {
-        ENF_TRY(enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
+        TIMED(TK_COUPLING, enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
                              h, pos, box, r_cut, mol_off, status, st));                           // :31
-        ENF_TRY(enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
+        TIMED(TK_COUPLING, enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
     }
     if (quantize) ENF_TRY(enf_argmax_reverse(h, d.N, nf, st));                                    // :35
     return ENF_OK;

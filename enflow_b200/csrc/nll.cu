@@ -129,10 +129,10 @@ int enf_nll_fwd(const float* pos, const float* vel, const float* h, const float*
     const size_t smem = sizeof(float) * 3 * (size_t)max_n;
     ENF_CHECK_ARG(smem <= 200 * 1024, "nll: molecule with %d atoms does not fit shared memory", max_n);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_nll<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_nll<false><<<B, TPB, smem, st>>>(pos, vel, h, g, mol_off, nf, kBT, softening, mol_term, nullptr, 0.f, nullptr,
+    enf_count_launch(), k_nll<false><<<B, TPB, smem, st>>>(pos, vel, h, g, mol_off, nf, kBT, softening, mol_term, nullptr, 0.f, nullptr,
                                        nullptr, nullptr, nullptr);
     const double logZ = -(double)N * (log((double)z_lj) - 1.5 * log(2.0 * M_PI / (double)kBT));
-    k_loss<<<1, 256, 0, st>>>(mol_term, B, ldj, logZ, loss);
+    enf_count_launch(), k_loss<<<1, 256, 0, st>>>(mol_term, B, ldj, logZ, loss);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -144,15 +144,15 @@ int enf_nll_bwd(const float* pos, const float* vel, const float* h, const float*
     const size_t smem = sizeof(float) * 3 * (size_t)max_n;
     ENF_CHECK_ARG(smem <= 200 * 1024, "nll: molecule with %d atoms does not fit shared memory", max_n);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_nll<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_nll<true><<<B, TPB, smem, st>>>(pos, vel, h, g, mol_off, nf, kBT, softening, nullptr, dloss, 1.0f / (float)B,
+    enf_count_launch(), k_nll<true><<<B, TPB, smem, st>>>(pos, vel, h, g, mol_off, nf, kBT, softening, nullptr, dloss, 1.0f / (float)B,
                                       dpos, dvel, dh, dg);
-    k_neg_scale<<<1, 1, 0, st>>>(dloss, 1.0f / (float)B, dldj);
+    enf_count_launch(), k_neg_scale<<<1, 1, 0, st>>>(dloss, 1.0f / (float)B, dldj);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
 
 int enf_ldj_total(const float* ldj_mol, int B, const float* log_q, float* ldj, cudaStream_t st) {
-    k_ldj_total<<<1, 256, 0, st>>>(ldj_mol, B, log_q, ldj);
+    enf_count_launch(), k_ldj_total<<<1, 256, 0, st>>>(ldj_mol, B, log_q, ldj);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

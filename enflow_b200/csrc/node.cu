@@ -316,7 +316,7 @@ int enf_pack_layer(const float* layer_params, int nf, float* packed, cudaStream_
     const EgclOffsets o = enf_egcl_offsets(nf);
     const PackOffsets p = enf_pack_offsets(nf);
     const int total = (nf + ENF_H) * ENF_H;
-    k_transpose_pack<<<(total + 255) / 256, 256, 0, st>>>(layer_params + o.off[P_W2], layer_params + o.off[P_W3],
+    enf_count_launch(), k_transpose_pack<<<(total + 255) / 256, 256, 0, st>>>(layer_params + o.off[P_W2], layer_params + o.off[P_W3],
                                                           layer_params + o.off[P_W4], nf, packed + p.w2t,
                                                           packed + p.w3t, packed + p.w4t);
     ENF_CHECK_LAUNCH();
@@ -326,7 +326,7 @@ int enf_pack_layer(const float* layer_params, int nf, float* packed, cudaStream_
 int enf_node_pre_fwd(const float* h, int N, int nf, const float* lp, float* P, float* S, float* Q, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
-    k_node_pre_fwd<<<enf_node_grid(N), TPB, 0, st>>>(h, N, nf, lp + o.off[P_W1], lp + o.off[P_B1], lp + o.off[P_W6],
+    enf_count_launch(), k_node_pre_fwd<<<enf_node_grid(N), TPB, 0, st>>>(h, N, nf, lp + o.off[P_W1], lp + o.off[P_B1], lp + o.off[P_W6],
                                                      lp + o.off[P_B6], lp + o.off[P_W7], lp + o.off[P_B7], P, S, Q);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
@@ -341,7 +341,7 @@ int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const int grid = enf_node_grid(N);
-    k_node_pre_bwd<<<grid, TPB, 0, st>>>(h, N, nf, lp + o.off[P_W1], lp + o.off[P_W6], lp + o.off[P_B6],
+    enf_count_launch(), k_node_pre_bwd<<<grid, TPB, 0, st>>>(h, N, nf, lp + o.off[P_W1], lp + o.off[P_W6], lp + o.off[P_B6],
                                          lp + o.off[P_W7], dP, dS, dQ, dh, partial);
     SegTable s;
     const int e1 = 2 * nf + 1;
@@ -351,7 +351,7 @@ int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float
     const int dsts[6] = {(int)o.off[P_W1], (int)o.off[P_B1], (int)o.off[P_W6], (int)o.off[P_B6], (int)o.off[P_W7],
                          (int)o.off[P_B7]};
     for (int i = 0; i < 6; ++i) { s.src[i] = src; s.dst[i] = dsts[i]; s.len[i] = lens[i]; src += lens[i]; }
-    k_reduce_partials<<<(src + 255) / 256, 256, 0, st>>>(partial, grid, src, s, lgrad);
+    enf_count_launch(), k_reduce_partials<<<(src + 255) / 256, 256, 0, st>>>(partial, grid, src, s, lgrad);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -366,7 +366,7 @@ int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const flo
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const PackOffsets p = enf_pack_offsets(nf);
-    k_node_post_fwd<<<enf_node_grid(N), TPB, node_post_fwd_smem(nf), st>>>(
+    enf_count_launch(), k_node_post_fwd<<<enf_node_grid(N), TPB, node_post_fwd_smem(nf), st>>>(
         h, agg, N, nf, packed + p.w4t, lp + o.off[P_B4], lp + o.off[P_W5], lp + o.off[P_B5], z4, G);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
@@ -392,7 +392,7 @@ int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const f
         cudaFuncSetAttribute(k_node_post_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
-    k_node_post_bwd<<<grid, TPB, node_post_bwd_smem(nf), st>>>(h, agg, z4, dG, N, nf, lp + o.off[P_W4],
+    enf_count_launch(), k_node_post_bwd<<<grid, TPB, node_post_bwd_smem(nf), st>>>(h, agg, z4, dG, N, nf, lp + o.off[P_W4],
                                                                lp + o.off[P_W5], dagg, dh, partial);
     SegTable s;
     const int D = nf + ENF_H;
@@ -401,7 +401,7 @@ int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const f
     int src = 0;
     s.n = 4;
     for (int i = 0; i < 4; ++i) { s.src[i] = src; s.dst[i] = dsts[i]; s.len[i] = lens[i]; src += lens[i]; }
-    k_reduce_partials<<<(src + 255) / 256, 256, 0, st>>>(partial, grid, src, s, lgrad);
+    enf_count_launch(), k_reduce_partials<<<(src + 255) / 256, 256, 0, st>>>(partial, grid, src, s, lgrad);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

@@ -83,11 +83,11 @@ int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, i
     if (N == 0) return ENF_OK;
     const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
     if (perm) {
-        if (apply_silu) k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
-        else k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        if (apply_silu) enf_count_launch(), k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        else enf_count_launch(), k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
     } else {
-        if (apply_silu) k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
-        else k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        if (apply_silu) enf_count_launch(), k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        else enf_count_launch(), k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
     }
     ENF_CHECK_LAUNCH();
     return ENF_OK;
@@ -97,8 +97,8 @@ int enf_segment_sum3(const float* x, const int* ptr, const int* perm, int N, int
                      int accumulate, float* out, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
-    if (perm) k_segment_sum3<true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, mean, scale, accumulate, out);
-    else k_segment_sum3<false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, mean, scale, accumulate, out);
+    if (perm) enf_count_launch(), k_segment_sum3<true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, mean, scale, accumulate, out);
+    else enf_count_launch(), k_segment_sum3<false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, mean, scale, accumulate, out);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

@@ -77,7 +77,11 @@ class Data:
         return self._map(lambda t: t.clone())
 
     def to(self, device):
-        return self._map(lambda t: t.to(device, non_blocking=True), device=device)
+        out = self._map(lambda t: t.to(device, non_blocking=True), device=device)
+        if self.N is not None and not self.N.is_cuda and self.N.ndim:
+            B, off, max_n, n_cpu = self.meta()           # computed on the host: no device sync later
+            out._meta = (B, off.to(device, non_blocking=True), max_n, n_cpu)
+        return out
 
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())

@@ -40,6 +40,17 @@ const char* enflow_last_error(void);
 int enflow_version(void);
 int enflow_hidden(void);
 
+/* ---- instrumentation (used by bench.py) ---------------------------------------------------------
+ * enflow_launch_count: kernels launched by this library since the last reset.
+ * enflow_timing_*: when enabled, the flow entry points bracket each kernel family with CUDA events on
+ * the launch stream; enflow_timing_read sums the elapsed milliseconds per family (host arrays of
+ * enflow_timing_kinds() entries; order: edges, node_pre, edge_fwd, segment_sum128, segment_sum3,
+ * node_post, coupling, edge_bwd, node_bwd, col_perm, argmax, nll). */
+long long enflow_launch_count(int reset);
+int enflow_timing_enable(int enable);
+int enflow_timing_kinds(void);
+int enflow_timing_read(float* ms, int* counts);
+
 /* ---- flat parameter buffer -------------------------------------------------------------------
  * All parameters of LFIntegrator(networks=L x EGCL, dequantize=ArgMax) live in ONE fp32 buffer
  * (gradients in a second one with the same layout, so data-parallel training needs one all-reduce).
