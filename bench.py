@@ -137,6 +137,7 @@ def main():
     ap.add_argument('--config', default='c2', choices=list(CONFIGS))
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp32_tc', 'bf16'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
@@ -165,6 +166,7 @@ def main():
     model = LFIntegrator([EGCL(nf, nf, H) for _ in range(L_LAYERS)], ArgMax(nf, H), dt=syn.TRAIN_DT)
     model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
     model = model.to(dev)
+    model.precision = args.precision
     if world > 1:
         dist.broadcast(model.flat_params, 0)
         model._dp_group = dist.group.WORLD
@@ -275,7 +277,7 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': desc, 'per_gpu_batch': batch, 'global_batch': mols, 'atoms_per_gpu': n_atoms,
-                       'edges_per_layer_per_gpu': E, 'layers': L_LAYERS, 'hidden': H, 'nf': nf,
+                       'edges_per_layer_per_gpu': E, 'layers': L_LAYERS, 'hidden': H, 'nf': nf, 'edge_mlp': args.precision,
                        'step': 'forward + Alchemical_NLL + backward (all parameter grads)'
                                + (' + NCCL all-reduce of the flat gradient buffer' if world > 1 else '') + ' + Adam',
                        'parallelism': f'dp{world}', 'l2': 'no explicit flush: every step streams the saved edge '

@@ -18,7 +18,7 @@ vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 class Dims(C.Structure):
     """enflow_dims_t"""
     _fields_ = [('B', i32), ('N', i32), ('nf', i32), ('L', i32), ('E_cap', i32), ('max_n', i32),
-                ('dt', f32), ('coords_weight', f32)]
+                ('dt', f32), ('coords_weight', f32), ('mode', i32)]
 
 
 # name -> (restype, argtypes); mirrors include/enflow_b200.h one to one
@@ -40,6 +40,9 @@ SIGNATURES = {
     'enflow_pack_layer': (i32, [vp, i32, vp, vp]),
     'enflow_node_pre_fwd': (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
     'enflow_edge_fwd': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    'enflow_tc_pack_bytes': (i64, []),
+    'enflow_tc_pack_layer': (i32, [vp, i32, vp, vp]),
+    'enflow_edge_fwd_tc': (i32, [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     'enflow_node_post_fwd': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp]),
     'enflow_coupling_fwd': (i32, [vp] * 9 + [i32, i32, f32] + [vp] * 6),
     'enflow_coupling_bwd': (i32, [vp, vp, vp, i32, i32, f32] + [vp] * 8),
@@ -118,3 +121,6 @@ def timing_read():
     cnt = (i32 * n)()
     check(lib().enflow_timing_read(ms, cnt))
     return {TIMING_KINDS[k]: (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+
+MODES = {'fp32': 0, 'fp32_tc': 1, 'bf16': 2}

@@ -139,6 +139,18 @@ int enflow_edge_fwd(const int* row, const int* col, const int* E_dev, int E_cap,
                     float* z2, float* z3, float* s, float* trans, void* stream) {
     return enf_edge_fwd(row, col, E_dev, E_cap, pos, box, P, S, lp, packed, nf, wr, z2, z3, s, trans, ST(stream));
 }
+int64_t enflow_tc_pack_bytes(void) { return enf_tc_pack_bytes(); }
+int enflow_tc_pack_layer(const float* lp, int nf, void* img, void* stream) {
+    return enf_tc_pack_layer(lp, nf, (unsigned char*)img, ST(stream));
+}
+int enflow_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
+                       const float* box, const float* P, const float* S, const float* lp, const void* wimg, int nf,
+                       float* z2, float* z3, float* s, float* trans, void* stream) {
+    ENF_CHECK_ARG(mode == 1 || mode == 2, "edge_fwd_tc: mode must be 1 (split) or 2 (bf16)");
+    ENF_CHECK_ARG((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "edge_fwd_tc: weight image must be 16-byte aligned");
+    return enf_edge_fwd_tc(mode, row, col, E_dev, E_cap, pos, box, P, S, lp, (const unsigned char*)wimg, nf, z2, z3, s,
+                           trans, ST(stream));
+}
 int enflow_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* lp, const float* packed,
                          float* z4, float* G, void* stream) {
     return enf_node_post_fwd(h, agg, N, nf, lp, packed, z4, G, ST(stream));

@@ -7,6 +7,7 @@
 struct enflow_dims_t {
     int32_t B, N, nf, L, E_cap, max_n;
     float dt, coords_weight;
+    int32_t mode;      // 0 = fp32 on the FFMA pipe, 1 = tcgen05 bf16x3 split (fp32-accurate), 2 = tcgen05 bf16
 };
 
 #define TIMED(kind, call)        \
@@ -41,6 +42,7 @@ struct Workspace {
     float *h[17], *g[17], *pos[17], *vel[17];
     LayerSave layer[16];
     float* packed;           // L * pack size
+    unsigned char* tcimg;    // L * swizzled bf16 weight images for the tcgen05 kernels
     float *P, *S, *F, *G, *trans, *wr;
     int* edges_ws;
     float* logq_atom;
@@ -80,6 +82,7 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
         s.agg = b.take<float>(N * H); s.z4 = b.take<float>(N * H);
     }
     w.packed = b.take<float>((size_t)d.L * enf_pack_offsets(d.nf).size);
+    w.tcimg = b.take<unsigned char>((size_t)d.L * enf_tc_pack_bytes() + 1024);
     w.P = b.take<float>(N * H); w.S = b.take<float>(N * H);
     w.F = b.take<float>(N * 3); w.G = b.take<float>(N * nf);
     w.trans = b.take<float>(E * 3); w.wr = b.take<float>(H);
@@ -102,6 +105,7 @@ int check_dims(const enflow_dims_t* d) {
     ENF_CHECK_ARG(d->nf >= 1 && d->nf <= ENF_MAX_NF, "nf=%d outside [1,%d]", d->nf, ENF_MAX_NF);
     ENF_CHECK_ARG(d->L >= 1 && d->L <= 16, "L=%d outside [1,16]", d->L);
     ENF_CHECK_ARG(d->B >= 0 && d->N >= 0 && d->E_cap >= 0, "negative size");
+    ENF_CHECK_ARG(d->mode >= 0 && d->mode <= 2, "mode=%d outside [0,2]", d->mode);
     return ENF_OK;
 }
 
@@ -110,19 +114,28 @@ float* layer_params(float* params, int nf, int l) { return params + (int64_t)l *
 const float* argmax_params(const float* params, int nf, int L) { return params + (int64_t)L * enf_egcl_offsets(nf).size; }
 float* argmax_params(float* params, int nf, int L) { return params + (int64_t)L * enf_egcl_offsets(nf).size; }
 
+unsigned char* tc_image(const Workspace& w, int l) {      // 1024-byte aligned: bulk copies need 16
+    unsigned char* base = w.tcimg + ((1024 - (reinterpret_cast<uintptr_t>(w.tcimg) & 1023)) & 1023);
+    return base + (int64_t)l * enf_tc_pack_bytes();
+}
+
 void copy_f(float* dst, const float* src, size_t n, cudaStream_t st) {
     if (dst != src && n) cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
 }
 
 // Q, F, G of one EGCL at the given node state (egcl.py:77-93); saves activations into `sv`
 int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv, const float* lp, const float* packed,
-                 const float* h, const float* pos, const float* box, const float* r_cut, const int* mol_off,
+                 const unsigned char* tcimg, const float* h, const float* pos, const float* box, const float* r_cut, const int* mol_off,
                  int* status, cudaStream_t st) {
     TIMED(TK_EDGES, enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
                                      sv.E_dev, status, w.edges_ws, st));
     TIMED(TK_NODE_PRE, enf_node_pre_fwd(h, d.N, d.nf, lp, w.P, w.S, sv.Q, st));
-    TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr, sv.z2, sv.z3,
-                         sv.s, w.trans, st));
+    if (d.mode == 0)
+        TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr,
+                                        sv.z2, sv.z3, sv.s, w.trans, st));
+    else
+        TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, tcimg, d.nf,
+                                           sv.z2, sv.z3, sv.s, w.trans, st));
     TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
     TIMED(TK_SEG3, enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
     TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
@@ -150,8 +163,10 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
     const int nf = d.nf;
     const size_t N = d.N;
     cudaMemsetAsync(ldj_mol, 0, sizeof(float) * d.B, st);
-    for (int l = 0; l < d.L; ++l)
+    for (int l = 0; l < d.L; ++l) {
         ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
+        if (d.mode) ENF_TRY(enf_tc_pack_layer(layer_params(params, nf, l), nf, tc_image(w, l), st));
+    }
     // state entering layer 0: dequantised h (dynamics.py:11), everything else copied
     if (eps) {
         TIMED(TK_ARGMAX, enf_argmax_fwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), mol_off, d.B, w.h[0], w.logq_atom,
@@ -172,7 +187,7 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
         float* vo = last ? vel_out : w.vel[nxt];
         const LayerSave& sv = w.layer[training ? l : 0];
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
-                             w.h[cur], w.pos[cur], box, r_cut, mol_off, status, st));
+                             tc_image(w, l), w.h[cur], w.pos[cur], box, r_cut, mol_off, status, st));
         TIMED(TK_COUPLING, enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
                                  ho, go, po, vo, ldj_mol, st));
     }
@@ -229,13 +244,15 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
     ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
     const int nf = d.nf;
     if (neg_ldj_mol) cudaMemsetAsync(neg_ldj_mol, 0, sizeof(float) * d.B, st);
-    for (int l = 0; l < d.L; ++l)
+    for (int l = 0; l < d.L; ++l) {
         ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
+        if (d.mode) ENF_TRY(enf_tc_pack_layer(layer_params(params, nf, l), nf, tc_image(w, l), st));
+    }
     const LayerSave& sv = w.layer[0];
     for (int l = d.L - 1; l >= 0; --l) {
         TIMED(TK_COUPLING, enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
-                             h, pos, box, r_cut, mol_off, status, st));                           // :31
+                             tc_image(w, l), h, pos, box, r_cut, mol_off, status, st));                           // :31
         TIMED(TK_COUPLING, enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
     }
     if (quantize) ENF_TRY(enf_argmax_reverse(h, d.N, nf, st));                                    // :35

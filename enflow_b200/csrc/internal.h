@@ -59,3 +59,10 @@ int enf_nll_bwd(const float* pos, const float* vel, const float* h, const float*
                 int max_n, float kBT, float softening, const float* dloss, float* dpos, float* dvel, float* dh,
                 float* dg, float* dldj, cudaStream_t st);
 int enf_ldj_total(const float* ldj_mol, int B, const float* log_q, float* ldj, cudaStream_t st);
+
+// tensor-core (tcgen05) edge kernels; mode 1 = bf16x3 split (fp32-accurate), mode 2 = bf16
+int64_t enf_tc_pack_bytes();
+int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t st);
+int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
+                    const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
+                    int nf, float* z2, float* z3, float* s_out, float* trans, cudaStream_t st);

@@ -32,7 +32,7 @@ class _FlowFn(torch.autograd.Function):
         dev = b['dev']
         nf = flow.networks[0].input_nf
         dims = _lib.Dims(b['B'], b['N'], nf, len(flow.networks), cap, b['max_n'], float(flow.dt),
-                         float(flow.networks[0].coords_weight))
+                         float(flow.networks[0].coords_weight), _lib.MODES[flow.precision])
         nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), int(training))
         ws = flow._take_workspace(nbytes, dev, training)
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -86,6 +86,9 @@ class LFIntegrator(BaseFlow):
         self._dp_group = None
         self.check_status = True
         self.last_status = None
+        # edge-MLP arithmetic: 'fp32' (FFMA pipe), 'fp32_tc' (tcgen05, bf16x3 operand split, fp32-accurate),
+        # 'bf16' (tcgen05, bf16 operands; the north star's bf16-MLP mode, tolerance 1e-2)
+        self.precision = 'fp32'
 
     # ---- workspace: one cached buffer, a fresh one if a pending backward still owns the cached one
     def _take_workspace(self, nbytes, dev, training):
@@ -162,7 +165,7 @@ class LFIntegrator(BaseFlow):
         p = _lib.ptr
         while True:
             dims = _lib.Dims(b['B'], b['N'], nf, len(self.networks), cap, b['max_n'], float(self.dt),
-                             float(self.networks[0].coords_weight))
+                             float(self.networks[0].coords_weight), _lib.MODES[self.precision])
             nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), 0)
             ws = self._take_workspace(nbytes, dev, False)
             neg = torch.empty(b['B'], dtype=torch.float32, device=dev)

@@ -38,6 +38,7 @@ class EGCL(nn.Module):
         self.coord_nn = nn.Sequential(nn.Linear(hidden_nf, hidden_nf), act_fn, last)
         self.vel_scaling_nn = nn.Sequential(nn.Linear(input_nf, hidden_nf), act_fn, nn.Linear(hidden_nf, 1))
         self._flat_view = None     # set by BaseFlow when the layer lives inside the flat parameter buffer
+        self.precision = 'fp32'    # see LFIntegrator.precision
 
     def _layer_flat(self, device):
         if self._flat_view is not None and self._flat_view.device == device:
@@ -78,8 +79,15 @@ class EGCL(nn.Module):
         p = _lib.ptr
         _lib.check(L.enflow_pack_layer(p(lp), nf, p(packed), st))
         _lib.check(L.enflow_node_pre_fwd(p(hf), N, nf, p(lp), p(P), p(S), p(Q), st))
-        _lib.check(L.enflow_edge_fwd(p(row), p(col), p(e_dev), E, p(pos), p(box), p(P), p(S), p(lp), p(packed), nf,
-                                     p(wr), p(z2), p(z3), p(s), p(trans), st))
+        mode = _lib.MODES[self.precision]
+        if mode == 0:
+            _lib.check(L.enflow_edge_fwd(p(row), p(col), p(e_dev), E, p(pos), p(box), p(P), p(S), p(lp), p(packed), nf,
+                                         p(wr), p(z2), p(z3), p(s), p(trans), st))
+        else:
+            wimg = torch.empty(L.enflow_tc_pack_bytes(), dtype=torch.uint8, device=dev)
+            _lib.check(L.enflow_tc_pack_layer(p(lp), nf, p(wimg), st))
+            _lib.check(L.enflow_edge_fwd_tc(mode, p(row), p(col), p(e_dev), E, p(pos), p(box), p(P), p(S), p(lp),
+                                            p(wimg), nf, p(z2), p(z3), p(s), p(trans), st))
         _lib.check(L.enflow_segment_sum128(p(z2), p(rowptr), None, N, E, 1, p(agg), st))
         _lib.check(L.enflow_segment_sum3(p(trans), p(rowptr), None, N, E, 1, float(self.coords_weight), 0, p(F), st))
         _lib.check(L.enflow_node_post_fwd(p(hf), p(agg), N, nf, p(lp), p(packed), p(z4), p(G), st))

@@ -34,6 +34,7 @@ typedef struct {
     int32_t max_n;         /* atoms in the largest molecule                            */
     float dt;              /* leap-frog step in LJ time units                          */
     float coords_weight;   /* EGCL coords_weight (egcl.py:11), 1.0 in Main             */
+    int32_t mode;          /* edge-MLP arithmetic: 0 = fp32 FFMA, 1 = tcgen05 bf16x3 split (fp32-accurate), 2 = tcgen05 bf16 */
 } enflow_dims_t;
 
 const char* enflow_last_error(void);
@@ -91,6 +92,14 @@ int enflow_node_pre_fwd(const float* h, int N, int nf, const float* layer_params
 int enflow_edge_fwd(const int32_t* row, const int32_t* col, const int32_t* E_dev, int E_cap, const float* pos,
                     const float* box, const float* P, const float* S, const float* layer_params, const float* packed,
                     int nf, float* wr_scratch, float* z2, float* z3, float* s, float* trans, void* stream);
+/* tensor-core variant of enflow_edge_fwd (tcgen05.mma, TMEM accumulators). wimg: enflow_tc_pack_bytes() bytes
+ * written by enflow_tc_pack_layer (swizzled bf16 hi/lo images of edge_nn.2 / coord_nn.0 weights), 16-byte aligned.
+ * mode 1: bf16x3 operand split, fp32-accurate; mode 2: plain bf16 operands. */
+int64_t enflow_tc_pack_bytes(void);
+int enflow_tc_pack_layer(const float* layer_params, int nf, void* wimg, void* stream);
+int enflow_edge_fwd_tc(int mode, const int32_t* row, const int32_t* col, const int32_t* E_dev, int E_cap,
+                       const float* pos, const float* box, const float* P, const float* S, const float* layer_params,
+                       const void* wimg, int nf, float* z2, float* z3, float* s, float* trans, void* stream);
 int enflow_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* layer_params,
                          const float* packed, float* z4, float* G, void* stream);
 

@@ -10,11 +10,15 @@ from enflow_b200.nn.egcl import EGCL
 DEV = 'cuda:0'
 
 
-def build_model(sd, nf, L, H=128, dt=None):
+def build_model(sd, nf, L, H=128, dt=None, precision='fp32'):
     from enflow_b200.data import synthetic as syn
     m = LFIntegrator([EGCL(nf, nf, H) for _ in range(L)], ArgMax(nf, H), dt=syn.TRAIN_DT if dt is None else dt)
     m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
-    return m.to(DEV)
+    m = m.to(DEV)
+    m.precision = precision
+    for net in m.networks:
+        net.precision = precision
+    return m
 
 
 def gpu_batch(arrs, dtype=torch.float64):

@@ -230,3 +230,46 @@ def test_edge_cases_single_atom_and_tiny_molecules():
     for k, p in model.named_parameters():
         r = ref_grads[k].numpy()
         assert np.linalg.norm(to_np(p.grad) - r) <= GRAD_TOL * max(np.linalg.norm(r), 1e-12), k
+
+
+# ---- tensor-core (tcgen05) edge MLP: fp32-accurate split mode and bf16 mode -------------------------------
+TC_MODES = [('fp32_tc', FWD_TOL, GRAD_TOL), ('bf16', 1e-2, 5e-2)]
+
+
+@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('mode,tol,gtol', TC_MODES)
+def test_tc_egcl_layers_vs_golden(name, mode, tol, gtol):
+    c = load_case(name)
+    trace, _, _, _, z0, _ = oracle_trace(c)
+    model = build_model(c['sd'], c['nf'], c['L'], precision=mode)
+    arrs = dict(c['batch'])
+    h = z0.numpy()
+    for i in range(c['L']):
+        if i > 0:
+            arrs['pos'], h = trace[i - 1]['pos'].numpy(), trace[i - 1]['h'].numpy()
+        data = gpu_batch(arrs)
+        Q, F, G = model.networks[i](torch.as_tensor(h, device=DEV), data.edges)
+        for k, v in (('Q', Q), ('F', F), ('G', G)):
+            err = rel_err(to_np(v), c['gold'][f'{k}{i}'])
+            # the north star bounds latents and log-likelihood (checked in the flow tests at `tol`); the raw
+            # per-layer force is a cancelling mean over edges and is held to 5x that here
+            assert err < 5 * tol, f'{mode} layer {i} {k}: rel err {err:.3e}'
+
+
+@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('mode,tol,gtol', TC_MODES)
+def test_tc_flow_train_step_vs_oracle(name, mode, tol, gtol):
+    from enflow_b200.flow.loss import Alchemical_NLL
+    c = load_case(name)
+    model = build_model(c['sd'], c['nf'], c['L'], precision=mode)
+    out, ldj = model(gpu_batch(c['batch']), eps=torch.as_tensor(c['eps']))
+    loss = Alchemical_NLL(kBT=c['kBT'], softening=c['softening'])(out, ldj)
+    loss.backward()
+    for k in ('h', 'g', 'pos', 'vel'):
+        err = rel_err(to_np(getattr(out, k)), c['gold'][f'out_{k}'])
+        assert err < tol, f'{mode} {k}: rel err {err:.3e}'
+    assert abs(loss.item() - float(c['gold']['loss'])) <= tol * abs(float(c['gold']['loss']))
+    _, ref_grads, _, _, _ = orc.train_step(c['sd'], c['L'], c['batch'], c['dt'], c['eps'], c['kBT'], c['softening'])
+    worst = sorted(((np.linalg.norm(to_np(p.grad) - ref_grads[k].numpy()) / max(np.linalg.norm(ref_grads[k].numpy()), 1e-300), k)
+                    for k, p in model.named_parameters()), reverse=True)
+    assert worst[0][0] < gtol, f'{mode} worst gradient errors: {worst[:5]}'
