@@ -485,6 +485,15 @@ __global__ void k_extract_wr(const float* __restrict__ W1, int e1, float* __rest
 static size_t fwd_smem() { return sizeof(float) * (TILE_FLOATS + 2 * KC * ENF_H) + sizeof(EdgeInfo); }
 static size_t bwd_smem() { return sizeof(float) * (2 * TILE_FLOATS + 2 * KC * ENF_H) + sizeof(EdgeInfo); }
 
+int enf_edge_reduce_partials(const float* partial, int n_cta, float* lgrad, int nf, cudaStream_t st) {
+    const EgclOffsets o = enf_egcl_offsets(nf);
+    enf_count_launch(), k_edge_reduce<<<(EDGE_PARTIAL + 255) / 256, 256, 0, st>>>(
+        partial, n_cta, (int)o.off[P_W2], (int)o.off[P_W3], (int)o.off[P_B2], (int)o.off[P_B3], (int)o.off[P_WC],
+        (int)o.off[P_W1], 2 * nf + 1, lgrad);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
 int enf_edge_fwd_grid() { return enf_num_sms() * 2; }
 int enf_edge_bwd_grid() { return enf_num_sms(); }
 int64_t enf_edge_partial_floats() { return (int64_t)enf_edge_bwd_grid() * EDGE_PARTIAL; }

@@ -82,22 +82,42 @@ __device__ __forceinline__ void store_chunk(unsigned char* A, int row, int chunk
     }
 }
 
-// D[m][n] (+)= sum_k A[m][k] W[n][k], both K-major images; SPLIT adds the two cross terms
-template <bool SPLIT>
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_base, uint32_t w_base, uint32_t idesc) {
+// D^T[n][e] (+)= sum_k W[n][k] X[e][k].  A = weight image (K-major, rows = output unit n); B = activation
+// image, either K-major (rows = edge e, cols = k: the x1 image) or MN-major (rows = k, cols = e: the x2^T image
+// the transposed epilogue writes).  SPLIT adds the two cross terms of the bf16 hi/lo operand split.
+template <bool SPLIT, bool B_MN>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t w_base, uint32_t x_base, uint32_t idesc) {
+    auto bdesc = [&](uint32_t base, int ks) { return B_MN ? tc::desc_mnmajor(base, ks) : tc::desc_kmajor(base, ks); };
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks)
-        tc::mma_f16(tmem_d, tc::desc_kmajor(a_base, ks), tc::desc_kmajor(w_base, ks), idesc, ks > 0);
+    for (int ks = 0; ks < 8; ++ks) tc::mma_f16(tmem_d, tc::desc_kmajor(w_base, ks), bdesc(x_base, ks), idesc, ks > 0);
     if (SPLIT) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)      // lo(A) . hi(W)
-            tc::mma_f16(tmem_d, tc::desc_kmajor(a_base + tc::IMG_BYTES, ks), tc::desc_kmajor(w_base, ks), idesc, true);
+        for (int ks = 0; ks < 8; ++ks)      // hi(W) . lo(X)
+            tc::mma_f16(tmem_d, tc::desc_kmajor(w_base, ks), bdesc(x_base + tc::IMG_BYTES, ks), idesc, true);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)      // hi(A) . lo(W)
-            tc::mma_f16(tmem_d, tc::desc_kmajor(a_base, ks), tc::desc_kmajor(w_base + tc::IMG_BYTES, ks), idesc, true);
+        for (int ks = 0; ks < 8; ++ks)      // lo(W) . hi(X)
+            tc::mma_f16(tmem_d, tc::desc_kmajor(w_base + tc::IMG_BYTES, ks), bdesc(x_base, ks), idesc, true);
     }
 }
 
+// 32x32 transpose-reduce across a warp: on return v[0] of lane l holds sum over lanes of (their) v[l]
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// Accumulators are TRANSPOSED: TMEM lane = hidden unit n, column = edge.  Thread (n, 32 edges) therefore keeps
+// its bias/weight scalars in registers, stores z rows fully coalesced (lanes = consecutive n), and writes the
+// next operand as the [hidden][edge] image (16-byte vector stores) that the second GEMM reads MN-major.
 template <bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ E_dev,
@@ -110,7 +130,6 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     unsigned char* sm = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
     unsigned char* Wimg = sm + L::w_off;
     unsigned char* A = sm + L::a_off;
-    Consts& cs = *reinterpret_cast<Consts*>(sm + L::c_off);
     TileInfo& ti = *reinterpret_cast<TileInfo*>(sm + L::t_off);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
     uint64_t* bar_mma = bar_w + 1;
@@ -118,10 +137,9 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = w & 3, cg = w >> 2;
-    const int m = 32 * q + lane;           // edge row in the tile == TMEM lane
-    const int c0 = 32 * cg;                // first feature column of this thread
+    const int n = 32 * q + lane;           // hidden unit == TMEM lane
+    const int ec = 32 * cg;                // first edge (tile-local) of this thread's 32 columns
 
-    // ---- one-time setup: barriers, TMEM, resident weight images (TMA bulk copies), per-layer vectors
     if (tid == 0) {
         tc::mbar_init(bar_w, 1);
         tc::mbar_init(bar_mma, 1);
@@ -129,12 +147,9 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     }
     __syncwarp();
     if (w == 0) tc::tmem_alloc(tmem_slot, 128);
-    for (int i = tid; i < ENF_H; i += THREADS) {
-        cs.wr[i] = W1[i * e1 + e1 - 1];
-        cs.b2[i] = b2[i];
-        cs.b3[i] = b3[i];
-        cs.wc[i] = wc[i];
-    }
+    const float b2n = b2[n], b3n = b3[n], wcn = wc[n];
+    const float4 wr4 = make_float4(W1[(4 * lane + 0) * e1 + e1 - 1], W1[(4 * lane + 1) * e1 + e1 - 1],
+                                   W1[(4 * lane + 2) * e1 + e1 - 1], W1[(4 * lane + 3) * e1 + e1 - 1]);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -142,26 +157,25 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     if (tid == 0) {
         tc::mbar_expect_tx(bar_w, L::NW * tc::IMG_BYTES);
         for (int i = 0; i < L::NW; ++i) {
-            // global order: W2_hi, W2_lo, W3_hi, W3_lo ; resident order: same when SPLIT, else W2_hi, W3_hi
-            const int src = SPLIT ? i : 2 * i;
+            const int src = SPLIT ? i : 2 * i;      // global order: W2_hi, W2_lo, W3_hi, W3_lo
             tc::bulk_g2s(Wimg + (size_t)i * tc::IMG_BYTES, wimg + (size_t)src * tc::IMG_BYTES, tc::IMG_BYTES, bar_w);
         }
     }
     tc::mbar_wait(bar_w, 0);
 
-    const uint32_t a_base = tc::smem_u32(A);
+    const uint32_t x_base = tc::smem_u32(A);
     const uint32_t w2_base = tc::smem_u32(Wimg);
     const uint32_t w3_base = tc::smem_u32(Wimg + (size_t)(SPLIT ? 2 : 1) * tc::IMG_BYTES);
-    const uint32_t idesc = tc::make_idesc(false, false);
-    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
+    const uint32_t idesc_kk = tc::make_idesc(false, false);
+    const uint32_t idesc_kmn = tc::make_idesc(false, true);
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)ec;
     uint32_t parity = 0;
 
     const int E = E_dev[0];
     const int tiles = (E + tc::TILE - 1) / tc::TILE;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int e0 = tile * tc::TILE;
-        // ---- edge geometry (data/base.py:15-19, egcl.py:80)
-        if (tid < tc::TILE) {
+        if (tid < tc::TILE) {       // edge geometry (data/base.py:15-19, egcl.py:80)
             const int e = e0 + tid;
             const bool ok = e < E;
             int i = 0, j = 0;
@@ -177,89 +191,81 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             ti.r[tid] = d0 * d0 + d1 * d1 + d2 * d2;
         }
         __syncthreads();
-        const bool ok = ti.valid[m];
-        // ---- x1 = silu(P[row] + S[col] + w_r r) into the operand image
-        {
+        // ---- x1 = silu(P[row] + S[col] + w_r r): one warp per edge row, lanes = 4 consecutive features
+        //      (coalesced 512-byte row reads), written into the K-major [edge][feature] operand image
+#pragma unroll 2
+        for (int it = 0; it < tc::TILE / 16; ++it) {
+            const int m = w + 16 * it;
             const float r = ti.r[m];
-            const float* p = P + (int64_t)ti.row[m] * ENF_H + c0;
-            const float* s = S + (int64_t)ti.col[m] * ENF_H + c0;
+            const float4 p = __ldg(reinterpret_cast<const float4*>(P + (int64_t)ti.row[m] * ENF_H) + lane);
+            const float4 s = __ldg(reinterpret_cast<const float4*>(S + (int64_t)ti.col[m] * ENF_H) + lane);
+            float x[4] = {fmaf(wr4.x, r, p.x + s.x), fmaf(wr4.y, r, p.y + s.y), fmaf(wr4.z, r, p.z + s.z),
+                          fmaf(wr4.w, r, p.w + s.w)};
+            const bool ok = ti.valid[m];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float4 p0 = __ldg(reinterpret_cast<const float4*>(p + 8 * ch));
-                const float4 p1 = __ldg(reinterpret_cast<const float4*>(p + 8 * ch + 4));
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + 8 * ch));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + 8 * ch + 4));
-                const float4 w0 = *reinterpret_cast<const float4*>(cs.wr + c0 + 8 * ch);
-                const float4 w1 = *reinterpret_cast<const float4*>(cs.wr + c0 + 8 * ch + 4);
-                float x[8] = {fmaf(w0.x, r, p0.x + s0.x), fmaf(w0.y, r, p0.y + s0.y), fmaf(w0.z, r, p0.z + s0.z),
-                              fmaf(w0.w, r, p0.w + s0.w), fmaf(w1.x, r, p1.x + s1.x), fmaf(w1.y, r, p1.y + s1.y),
-                              fmaf(w1.z, r, p1.z + s1.z), fmaf(w1.w, r, p1.w + s1.w)};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = ok ? x[j] * tc::sigmoid_sfu(x[j]) : 0.f;
-                store_chunk<SPLIT>(A, m, 4 * cg + ch, x);
+            for (int j = 0; j < 4; ++j) x[j] = ok ? x[j] * tc::sigmoid_sfu(x[j]) : 0.f;
+            const uint32_t off = tc::img_chunk_offset(m, lane >> 1) + ((lane & 1) << 3);
+            if (SPLIT) {
+                uint2 hi, lo;
+                tc::split2(x[0], x[1], hi.x, lo.x);
+                tc::split2(x[2], x[3], hi.y, lo.y);
+                *reinterpret_cast<uint2*>(A + off) = hi;
+                *reinterpret_cast<uint2*>(A + tc::IMG_BYTES + off) = lo;
+            } else {
+                *reinterpret_cast<uint2*>(A + off) = make_uint2(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]));
             }
         }
         tc::fence_async_smem();
         __syncthreads();
-        // ---- z2 = x1 W2^T on the tensor core
-        if (tid == 0) {
+        if (tid == 0) {             // z2^T = W2 x1^T on the tensor core
             tc::fence_after_sync();
-            issue_gemm<SPLIT>(tmem, a_base, w2_base, idesc);
+            issue_gemm<SPLIT, false>(tmem, w2_base, x_base, idesc_kk);
             tc::mma_commit(bar_mma);
         }
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
-        // ---- epilogue 1: bias, save z2, x2 = silu(z2) back into the operand image
+        // ---- epilogue 1: bias, save z2 (coalesced: lanes = consecutive n), x2^T = silu(z2)^T as the next operand
         {
             float v[32];
             tc::tmem_ld32(taddr, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += cs.b2[c0 + j];
-            if (ok) {
-                float4* dst = reinterpret_cast<float4*>(z2 + (int64_t)(e0 + m) * ENF_H + c0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 32; ++j) {
+                v[j] += b2n;
+                const bool ok = ti.valid[ec + j];
+                if (ok) z2[(int64_t)(e0 + ec + j) * ENF_H + n] = v[j];
+                v[j] = ok ? v[j] * tc::sigmoid_sfu(v[j]) : 0.f;
             }
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 float x[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float z = v[8 * ch + j];
-                    x[j] = ok ? z * tc::sigmoid_sfu(z) : 0.f;
-                }
-                store_chunk<SPLIT>(A, m, 4 * cg + ch, x);
+                for (int j = 0; j < 8; ++j) x[j] = v[8 * ch + j];
+                store_chunk<SPLIT>(A, n, 4 * cg + ch, x);       // image row = hidden unit, columns = edges
             }
         }
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
-        // ---- z3 = x2 W3^T
-        if (tid == 0) {
+        if (tid == 0) {             // z3^T = W3 x2^T  (B read MN-major)
             tc::fence_after_sync();
-            issue_gemm<SPLIT>(tmem, a_base, w3_base, idesc);
+            issue_gemm<SPLIT, true>(tmem, w3_base, x_base, idesc_kmn);
             tc::mma_commit(bar_mma);
         }
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
-        // ---- epilogue 2: bias, save z3, s = wc . silu(z3)
+        // ---- epilogue 2: bias, save z3, s[e] = sum_n wc[n] silu(z3[e][n]) (transpose-reduce over the warp's 32 n)
         {
             float v[32];
             tc::tmem_ld32(taddr, v);
-            float part = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                v[j] += cs.b3[c0 + j];
-                part = fmaf(cs.wc[c0 + j], v[j] * tc::sigmoid_sfu(v[j]), part);
+                v[j] += b3n;
+                if (ti.valid[ec + j]) z3[(int64_t)(e0 + ec + j) * ENF_H + n] = v[j];
+                v[j] = wcn * (v[j] * tc::sigmoid_sfu(v[j]));
             }
-            if (ok) {
-                float4* dst = reinterpret_cast<float4*>(z3 + (int64_t)(e0 + m) * ENF_H + c0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            ti.s_part[cg][m] = part;
+            ti.s_part[q][ec + lane] = warp_transpose_sum(v, lane);
         }
         tc::fence_before_sync();
         __syncthreads();

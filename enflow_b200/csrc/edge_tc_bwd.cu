@@ -1,0 +1,406 @@
+// K1 backward on tcgen05: recompute + dgrad + wgrad of the two dense edge layers, per 64-edge tile,
+// without reading any saved [E,H] activation (enflow/nn/egcl.py:57-63,71-75 differentiated by hand).
+//
+// All GEMMs keep the accumulator TRANSPOSED (TMEM lane = hidden unit, column = edge or weight column):
+//   T1 [n][e] = W2 x1^T            A = W2 image (K-major)          B = x1 image   [e][k] (K-major)
+//   T2 [n][e] = W3 x2^T            A = W3 image (K-major)          B = x2^T image [k][e] (MN-major)
+//   TW3[n][k] += dz3^T x2          A = dz3^T image [n][e] (K-major) B = x2^T image [k][e] (K-major)
+//   T2 [k][e] = W3^T dz3^T         A = W3 image (MN-major)         B = dz3^T image [n][e] (MN-major)
+//   TW2[n][k] += dz2^T x1          A = dz2^T image [n][e] (K-major) B = x1 image   [e][k] (MN-major)
+//   T1 [k][e] = W2^T dz2^T         A = W2 image (MN-major)         B = dz2^T image [n][e] (MN-major)
+// One swizzled image per operand serves every view (tc_common.cuh).  The weight-gradient accumulators TW2/TW3
+// stay in TMEM for the whole life of the CTA and are written once at the end as a per-CTA partial; partials are
+// combined in CTA order (deterministic).  x1 is regenerated rather than kept: with the bf16x3 operand split
+// (hi/lo images) shared memory holds the two weight matrices (128 KB) plus two activation buffers (64 KB).
+//
+// Thread map: 16 warps; warp w owns TMEM lanes [32 (w%4), +32) = hidden units n and tile edges [16 (w/4), +16).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 512;
+constexpr int TE = 64;                     // edges per tile
+constexpr int ACT_IMG = 128 * TE * 2;      // one bf16 activation image: 16 KB
+constexpr int X1_BLK = TE * 128;           // block stride of the [e][k] image
+constexpr uint32_t T1_COL = 0, T2_COL = 64, TW2_COL = 128, TW3_COL = 256, TMEM_COLS = 512;
+
+struct TileInfoB {
+    int row[TE], col[TE], valid[TE];
+    float d[TE][3], r[TE], ds[TE], ddir[TE][3];
+    float dr_part[4][TE];
+};
+
+template <bool SPLIT>
+struct SmemB {
+    static constexpr int NW = SPLIT ? 4 : 2;
+    static constexpr int NA = SPLIT ? 2 : 1;
+    static constexpr size_t w_off = 0;
+    static constexpr size_t x_off = (size_t)NW * tc::IMG_BYTES;
+    static constexpr size_t z_off = x_off + (size_t)NA * ACT_IMG;
+    static constexpr size_t t_off = z_off + (size_t)NA * ACT_IMG;
+    static constexpr size_t bar_off = (t_off + sizeof(TileInfoB) + 15) / 16 * 16;
+    static constexpr size_t total = bar_off + 64 + 1024;
+};
+
+__device__ __forceinline__ uint32_t x1_off(int e, int chunk16) {          // [e][k] image, 64 rows
+    return (uint32_t)((chunk16 >> 3) * X1_BLK + e * 128 + (((chunk16 & 7) ^ (e & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t t_off_(int n, int chunk8) {           // [n][e] image, 128 rows x 64 cols
+    return (uint32_t)(n * 128 + ((chunk8 ^ (n & 7)) << 4));
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void store8(unsigned char* img, uint32_t off, const float (&x)[8]) {
+    if (SPLIT) {
+        uint4 hi, lo;
+        tc::split2(x[0], x[1], hi.x, lo.x);
+        tc::split2(x[2], x[3], hi.y, lo.y);
+        tc::split2(x[4], x[5], hi.z, lo.z);
+        tc::split2(x[6], x[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(img + off) = hi;
+        *reinterpret_cast<uint4*>(img + ACT_IMG + off) = lo;
+    } else {
+        uint4 hi;
+        hi.x = tc::pack_bf16(x[0], x[1]); hi.y = tc::pack_bf16(x[2], x[3]);
+        hi.z = tc::pack_bf16(x[4], x[5]); hi.w = tc::pack_bf16(x[6], x[7]);
+        *reinterpret_cast<uint4*>(img + off) = hi;
+    }
+}
+
+// generic 3-term (or 1-term) GEMM issue. da(base, ks) / db(base, ks) build the descriptors of one image;
+// lo images sit a_lo / b_lo bytes after the hi images.
+template <bool SPLIT, typename FA, typename FB>
+__device__ __forceinline__ void issue(uint32_t tmem_d, int ksteps, uint32_t a, uint32_t a_lo, uint32_t b, uint32_t b_lo,
+                                      uint32_t idesc, bool acc_first, FA da, FB db) {
+    for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16(tmem_d, da(a, ks), db(b, ks), idesc, acc_first || ks > 0);
+    if (SPLIT) {
+        for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16(tmem_d, da(a, ks), db(b + b_lo, ks), idesc, true);
+        for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16(tmem_d, da(a + a_lo, ks), db(b, ks), idesc, true);
+    }
+}
+
+// sum over the 32 lanes of 16 per-lane values; lane l receives column (l & 15)
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// Per-CTA partial layout (floats), identical to the FFMA kernel: dW2 [H*H] | dW3 [H*H] | db2 | db3 | dwc | dwr
+constexpr int EDGE_PARTIAL = 2 * ENF_H * ENF_H + 4 * ENF_H;
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(THREADS, 1)
+k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ rowptr,
+              const int* __restrict__ E_dev, const float* __restrict__ pos, const float* __restrict__ box,
+              const float* __restrict__ P, const float* __restrict__ S, const float* __restrict__ W1, int e1,
+              const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ wc,
+              const unsigned char* __restrict__ wimg, const float* __restrict__ s_saved,
+              const float* __restrict__ dagg, const float* __restrict__ dF, float coords_weight,
+              float* __restrict__ dz1, float* __restrict__ dd_out, float* __restrict__ partial) {
+    using L = SmemB<SPLIT>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
+    unsigned char* Wimg = sm + L::w_off;
+    unsigned char* XB = sm + L::x_off;         // x1 image [e][k], later x2^T image [k][e], later x1 again
+    unsigned char* ZB = sm + L::z_off;         // dz3^T then dz2^T image [n][e]
+    TileInfoB& ti = *reinterpret_cast<TileInfoB*>(sm + L::t_off);
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
+    uint64_t* bar_mma = bar_w + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int q = w & 3, cg = w >> 2;
+    const int n = 32 * q + lane;           // hidden unit == TMEM lane
+    const int ec = 16 * cg;                // first tile edge of this thread's 16 columns
+
+    if (tid == 0) {
+        tc::mbar_init(bar_w, 1);
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (w == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    const float b2n = b2[n], b3n = b3[n], wcn = wc[n], wrn = W1[n * e1 + e1 - 1];
+    const float4 wr4 = make_float4(W1[(4 * lane + 0) * e1 + e1 - 1], W1[(4 * lane + 1) * e1 + e1 - 1],
+                                   W1[(4 * lane + 2) * e1 + e1 - 1], W1[(4 * lane + 3) * e1 + e1 - 1]);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) {
+        tc::mbar_expect_tx(bar_w, L::NW * tc::IMG_BYTES);
+        for (int i = 0; i < L::NW; ++i) {
+            const int src = SPLIT ? i : 2 * i;      // global order: W2_hi, W2_lo, W3_hi, W3_lo
+            tc::bulk_g2s(Wimg + (size_t)i * tc::IMG_BYTES, wimg + (size_t)src * tc::IMG_BYTES, tc::IMG_BYTES, bar_w);
+        }
+    }
+    tc::mbar_wait(bar_w, 0);
+
+    const uint32_t xb = tc::smem_u32(XB), zb = tc::smem_u32(ZB);
+    const uint32_t w2 = tc::smem_u32(Wimg), w3 = tc::smem_u32(Wimg + (size_t)(SPLIT ? 2 : 1) * tc::IMG_BYTES);
+    const uint32_t WLO = tc::IMG_BYTES, ALO = ACT_IMG;
+    const uint32_t id_kk64 = tc::make_idesc(false, false, 64), id_kmn64 = tc::make_idesc(false, true, 64);
+    const uint32_t id_mm64 = tc::make_idesc(true, true, 64);
+    const uint32_t id_kk128 = tc::make_idesc(false, false, 128), id_kmn128 = tc::make_idesc(false, true, 128);
+    // descriptor builders for the image shapes in play
+    auto dW_k = [](uint32_t b, int ks) { return tc::desc_k(b, ks, tc::BLK_BYTES); };     // W [n][k] K-major
+    auto dW_mn = [](uint32_t b, int ks) { return tc::desc_mn(b, ks, tc::BLK_BYTES); };   // W read as [K=n][M=k]
+    auto dX1_k = [](uint32_t b, int ks) { return tc::desc_k(b, ks, X1_BLK); };           // x1 [e][k], K = k
+    auto dX1_mn = [](uint32_t b, int ks) { return tc::desc_mn(b, ks, X1_BLK); };         // x1 rows = K = e, N = k
+    auto dT_k = [](uint32_t b, int ks) { return tc::desc_k(b, ks, 0); };                 // [n][e], K = e (4 steps)
+    auto dT_mn = [](uint32_t b, int ks) { return tc::desc_mn(b, ks, tc::BLK_BYTES); };   // [n][e] rows = K = n, N = e
+
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
+    uint32_t parity = 0;
+    float gb2 = 0.f, gb3 = 0.f, gwc = 0.f, gwr = 0.f;
+    bool first_tile = true;
+
+    const int E = E_dev[0];
+    const int tiles = (E + TE - 1) / TE;
+
+    // x1 = silu(P[row] + S[col] + w_r r) into XB as the [e][k] image: one warp per edge row
+    auto gen_x1 = [&]() {
+#pragma unroll
+        for (int it = 0; it < TE / 16; ++it) {
+            const int m = w + 16 * it;
+            const float r = ti.r[m];
+            const float4 p = __ldg(reinterpret_cast<const float4*>(P + (int64_t)ti.row[m] * ENF_H) + lane);
+            const float4 s = __ldg(reinterpret_cast<const float4*>(S + (int64_t)ti.col[m] * ENF_H) + lane);
+            float x[4] = {fmaf(wr4.x, r, p.x + s.x), fmaf(wr4.y, r, p.y + s.y), fmaf(wr4.z, r, p.z + s.z),
+                          fmaf(wr4.w, r, p.w + s.w)};
+            const bool ok = ti.valid[m];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = ok ? x[j] * tc::sigmoid_sfu(x[j]) : 0.f;
+            const uint32_t off = x1_off(m, lane >> 1) + ((lane & 1) << 3);
+            if (SPLIT) {
+                uint2 hi, lo;
+                tc::split2(x[0], x[1], hi.x, lo.x);
+                tc::split2(x[2], x[3], hi.y, lo.y);
+                *reinterpret_cast<uint2*>(XB + off) = hi;
+                *reinterpret_cast<uint2*>(XB + ACT_IMG + off) = lo;
+            } else {
+                *reinterpret_cast<uint2*>(XB + off) = make_uint2(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]));
+            }
+        }
+    };
+    auto run_mma = [&](auto&& body) {            // one thread issues, everybody waits for completion
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            body();
+            tc::mma_commit(bar_mma);
+        }
+        tc::mbar_wait(bar_mma, parity);
+        parity ^= 1;
+        tc::fence_after_sync();
+    };
+
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * TE;
+        __syncthreads();
+        if (tid < TE) {
+            const int e = e0 + tid;
+            const bool ok = e < E;
+            int i = 0, j = 0;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, ds = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+            if (ok) {
+                i = row[e]; j = col[e];
+                d0 = wrapf_(pos[(int64_t)i * 3 + 0] - pos[(int64_t)j * 3 + 0], 0.5f * box[(int64_t)i * 3 + 0]);
+                d1 = wrapf_(pos[(int64_t)i * 3 + 1] - pos[(int64_t)j * 3 + 1], 0.5f * box[(int64_t)i * 3 + 1]);
+                d2 = wrapf_(pos[(int64_t)i * 3 + 2] - pos[(int64_t)j * 3 + 2], 0.5f * box[(int64_t)i * 3 + 2]);
+                const int deg = rowptr[i + 1] - rowptr[i];
+                const float sc = coords_weight / (float)(deg > 1 ? deg : 1);          // helpers.py:70 (Q12)
+                const float s = s_saved[e];
+                const float dv[3] = {d0, d1, d2};
+                float dtr[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float tr = dv[c] * s;
+                    const bool pass = (tr >= -100.f) && (tr <= 100.f);               // clamp backward mask
+                    dtr[c] = pass ? dF[(int64_t)i * 3 + c] * sc : 0.f;
+                    ds = fmaf(dtr[c], dv[c], ds);
+                }
+                q0 = dtr[0] * s; q1 = dtr[1] * s; q2 = dtr[2] * s;
+            }
+            ti.row[tid] = i; ti.col[tid] = j; ti.valid[tid] = ok;
+            ti.d[tid][0] = d0; ti.d[tid][1] = d1; ti.d[tid][2] = d2;
+            ti.r[tid] = d0 * d0 + d1 * d1 + d2 * d2;
+            ti.ds[tid] = ds;
+            ti.ddir[tid][0] = q0; ti.ddir[tid][1] = q1; ti.ddir[tid][2] = q2;
+        }
+        __syncthreads();
+        gen_x1();
+        // ---- T1 = W2 x1^T
+        run_mma([&]() { issue<SPLIT>(tmem + T1_COL, 8, w2, WLO, xb, ALO, id_kk64, false, dW_k, dX1_k); });
+        float z2r[16];
+        {
+            tc::tmem_ld16(lane_base + T1_COL + ec, z2r);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int jj = 8 * ch + j;
+                    z2r[jj] += b2n;
+                    x[j] = ti.valid[ec + jj] ? z2r[jj] * tc::sigmoid_sfu(z2r[jj]) : 0.f;
+                }
+                store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);          // x2^T image [k][e]
+            }
+        }
+        // ---- T2 = W3 x2^T
+        run_mma([&]() { issue<SPLIT>(tmem + T2_COL, 8, w3, WLO, xb, ALO, id_kmn64, false, dW_k, dT_mn); });
+        {
+            float v[16];
+            tc::tmem_ld16(lane_base + T2_COL + ec, v);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int jj = 8 * ch + j;
+                    const float z = v[jj] + b3n;
+                    const float sg = tc::sigmoid_sfu(z);
+                    const float ds = ti.ds[ec + jj];
+                    gwc = fmaf(ds, z * sg, gwc);
+                    const float dz = ds * wcn * (sg * (1.0f + z * (1.0f - sg)));
+                    gb3 += dz;
+                    x[j] = dz;
+                }
+                store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz3^T image [n][e]
+            }
+        }
+        // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T
+        run_mma([&]() {
+            issue<SPLIT>(tmem + TW3_COL, 4, zb, ALO, xb, ALO, id_kk128, !first_tile, dT_k, dT_k);
+            issue<SPLIT>(tmem + T2_COL, 8, w3, WLO, zb, ALO, id_mm64, false, dW_mn, dT_mn);
+        });
+        {
+            float v[16];
+            tc::tmem_ld16(lane_base + T2_COL + ec, v);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int jj = 8 * ch + j;
+                    const bool ok = ti.valid[ec + jj];
+                    const float da = ok ? __ldg(dagg + (int64_t)ti.row[ec + jj] * ENF_H + n) : 0.f;
+                    const float z = z2r[jj];
+                    const float sg = tc::sigmoid_sfu(z);
+                    const float dz = ok ? (v[jj] + da) * (sg * (1.0f + z * (1.0f - sg))) : 0.f;
+                    gb2 += dz;
+                    x[j] = dz;
+                }
+                store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz2^T image [n][e]
+            }
+        }
+        gen_x1();                                                       // x2^T is dead: rebuild x1 in XB
+        // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T
+        run_mma([&]() {
+            issue<SPLIT>(tmem + TW2_COL, 4, zb, ALO, xb, ALO, id_kmn128, !first_tile, dT_k, dX1_mn);
+            issue<SPLIT>(tmem + T1_COL, 8, w2, WLO, zb, ALO, id_mm64, false, dW_mn, dT_mn);
+        });
+        first_tile = false;
+        {
+            float v[16];
+            tc::tmem_ld16(lane_base + T1_COL + ec, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int m = ec + j;
+                const bool ok = ti.valid[m];
+                const float r = ti.r[m];
+                const float z = ok ? fmaf(wrn, r, __ldg(P + (int64_t)ti.row[m] * ENF_H + n) + __ldg(S + (int64_t)ti.col[m] * ENF_H + n)) : 0.f;
+                const float sg = tc::sigmoid_sfu(z);
+                const float dz = ok ? v[j] * (sg * (1.0f + z * (1.0f - sg))) : 0.f;
+                if (ok) dz1[(int64_t)(e0 + m) * ENF_H + n] = dz;
+                gwr = fmaf(dz, r, gwr);
+                v[j] = wrn * dz;
+            }
+            const float t = warp_transpose_sum16(v, lane);
+            if (lane < 16) ti.dr_part[q][ec + lane] = t;
+        }
+        __syncthreads();
+        if (tid < TE && ti.valid[tid]) {
+            const float dr2 = 2.0f * ((ti.dr_part[0][tid] + ti.dr_part[1][tid]) + (ti.dr_part[2][tid] + ti.dr_part[3][tid]));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dd_out[(int64_t)(e0 + tid) * 3 + c] = fmaf(dr2, ti.d[tid][c], ti.ddir[tid][c]);
+        }
+    }
+    // ---- per-CTA partials: weight gradients from TMEM, vector gradients combined over the 4 edge groups
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    float* my = partial + (int64_t)blockIdx.x * EDGE_PARTIAL;
+    {
+        float v[32];
+#pragma unroll 1
+        for (int mat = 0; mat < 2; ++mat) {
+            if (first_tile) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;        // this CTA had no tile: TMEM was never written
+            } else {
+                tc::tmem_ld32(lane_base + (mat ? TW3_COL : TW2_COL) + 32 * cg, v);
+            }
+            float4* dst = reinterpret_cast<float4*>(my + mat * ENF_H * ENF_H + n * ENF_H + 32 * cg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+    float* red = reinterpret_cast<float*>(XB);          // [4 kinds][4 cg][128]
+    red[(0 * 4 + cg) * ENF_H + n] = gb2;
+    red[(1 * 4 + cg) * ENF_H + n] = gb3;
+    red[(2 * 4 + cg) * ENF_H + n] = gwc;
+    red[(3 * 4 + cg) * ENF_H + n] = gwr;
+    __syncthreads();
+    if (tid < 4 * ENF_H) {
+        const int a = tid / ENF_H, k = tid % ENF_H;
+        my[2 * ENF_H * ENF_H + tid] = (red[(a * 4 + 0) * ENF_H + k] + red[(a * 4 + 1) * ENF_H + k]) +
+                                      (red[(a * 4 + 2) * ENF_H + k] + red[(a * 4 + 3) * ENF_H + k]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (w == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace
+
+int enf_edge_reduce_partials(const float* partial, int n_cta, float* lgrad, int nf, cudaStream_t st);
+
+int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
+                    const float* pos, const float* box, const float* P, const float* S, const float* lp,
+                    const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
+                    float coords_weight, float* dz1, float* dd, float* lgrad, float* partial, cudaStream_t st) {
+    if (E_cap == 0) return ENF_OK;
+    const EgclOffsets o = enf_egcl_offsets(nf);
+    const int grid = enf_num_sms();
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_edge_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemB<true>::total);
+        cudaFuncSetAttribute(k_edge_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemB<false>::total);
+        attr = true;
+    }
+    if (mode == 1)
+        enf_count_launch(), k_edge_bwd_tc<true><<<grid, THREADS, SmemB<true>::total, st>>>(
+            row, col, rowptr, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
+            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, dz1, dd, partial);
+    else
+        enf_count_launch(), k_edge_bwd_tc<false><<<grid, THREADS, SmemB<false>::total, st>>>(
+            row, col, rowptr, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
+            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, dz1, dd, partial);
+    ENF_CHECK_LAUNCH();
+    return enf_edge_reduce_partials(partial, grid, lgrad, nf, st);
+}

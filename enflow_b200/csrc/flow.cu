@@ -217,8 +217,14 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         TIMED(TK_NODE_PRE, enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
         TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
                                    w.edges_ws, st));
-        TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf, w.wr, sv.z2,
-                             sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg, w.partial, st));
+        if (d.mode == 0)
+            TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf,
+                                            w.wr, sv.z2, sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg,
+                                            w.partial, st));
+        else
+            TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P,
+                                               w.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1,
+                                               w.dd, lg, w.partial, st));
         TIMED(TK_SEG128, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
         TIMED(TK_SEG128, enf_segment_sum128(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, st));
         // coord_diff = pos[row] - pos[col] (data/base.py:17): +dd onto row atoms, -dd onto col atoms

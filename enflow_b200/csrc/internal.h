@@ -66,3 +66,7 @@ int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t 
 int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
                     const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
                     int nf, float* z2, float* z3, float* s_out, float* trans, cudaStream_t st);
+int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
+                    const float* pos, const float* box, const float* P, const float* S, const float* lp,
+                    const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
+                    float coords_weight, float* dz1, float* dd, float* lgrad, float* partial, cudaStream_t st);

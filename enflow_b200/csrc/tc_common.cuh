@@ -46,15 +46,23 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int ks) {
     return make_desc(base + ks * 2048, BLK_BYTES, 1024);
 }
 
+// general forms: `blk_stride` = bytes between the 64-column blocks of the image (rows * 128)
+__device__ __forceinline__ uint64_t desc_k(uint32_t base, int ks, uint32_t blk_stride) {
+    return make_desc(base + (ks >> 2) * blk_stride + (ks & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t base, int ks, uint32_t blk_stride) {
+    return make_desc(base + ks * 2048, blk_stride, 1024);
+}
+
 // ---- instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M = N = 128 --------------
-__device__ __forceinline__ uint32_t make_idesc(bool a_mn_major, bool b_mn_major) {
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn_major, bool b_mn_major, uint32_t n = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                       // c_format = F32
     d |= 1u << 7;                       // a_format = BF16
     d |= 1u << 10;                      // b_format = BF16
     d |= (a_mn_major ? 1u : 0u) << 15;
     d |= (b_mn_major ? 1u : 0u) << 16;
-    d |= (128u >> 3) << 17;             // N
+    d |= (n >> 3) << 17;                // N
     d |= (128u >> 4) << 24;             // M
     return d;
 }
@@ -100,6 +108,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
 // ---- mbarrier -------------------------------------------------------------------------------------------
