@@ -137,7 +137,7 @@ def main():
     ap.add_argument('--config', default='c2', choices=list(CONFIGS))
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp32_tc', 'bf16'])
+    ap.add_argument('--precision', default='fp32_tc', choices=['fp32', 'fp32_tc', 'bf16'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

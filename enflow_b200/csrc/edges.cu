@@ -20,21 +20,21 @@ __device__ __forceinline__ double shift_of(int idx, double L) {   // helpers.py:
     return idx == 0 ? -L : (idx == 1 ? L : 0.0);
 }
 
-__global__ void k_atom_mol(const int* __restrict__ mol_off, int B, int* __restrict__ atom_mol) {
-    int m = blockIdx.x;
-    if (m >= B) return;
-    for (int i = mol_off[m] + threadIdx.x; i < mol_off[m + 1]; i += blockDim.x) atom_mol[i] = m;
-}
-
-// One CTA per molecule: survivor flags of the 27n image points, ranked in (image, atom) order.
+// One CTA per molecule: survivor flags of the 27n image points, ranked in (image, atom) order, plus the
+// compact list of "active" survivors: those close enough to the molecule to have a hit at all.
+// The activity test is pure pruning against a bounding sphere (centre = mean position, radius = max distance,
+// margin ~1e6 ulp): every pair that is not discarded is still decided by the exact fp64 test.
 template <typename T>
 __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ pos, const T* __restrict__ box,
                                                           const float* __restrict__ r_cut,
                                                           const int* __restrict__ mol_off, int B,
                                                           int* __restrict__ qrank, int* __restrict__ idmap,
-                                                          int* __restrict__ nsurv) {
-    __shared__ int warp_tot[8];
-    __shared__ int running_s;
+                                                          int* __restrict__ nsurv, int* __restrict__ active,
+                                                          int* __restrict__ nactive) {
+    __shared__ int warp_tot[8], warp_act[8];
+    __shared__ int running_s, running_a;
+    __shared__ double red_s[8][3];
+    __shared__ double ctr_s[4];
     const int m = blockIdx.x;
     const int o = mol_off[m], n = mol_off[m + 1] - o;
     const int64_t base = 27LL * o;
@@ -42,12 +42,42 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
     const double bx = ld3(box, o, 0), by = ld3(box, o, 1), bz = ld3(box, o, 2);   // base.py:130 box[0]
     const double ex = __dadd_rn(bx, rc), ey = __dadd_rn(by, rc), ez = __dadd_rn(bz, rc);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) running_s = 0;
+    if (threadIdx.x == 0) { running_s = 0; running_a = 0; }
+    // ---- bounding sphere
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int a = threadIdx.x; a < n; a += 256) { sx += ld3(pos, o + a, 0); sy += ld3(pos, o + a, 1); sz += ld3(pos, o + a, 2); }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { red_s[wid][0] = sx; red_s[wid][1] = sy; red_s[wid][2] = sz; }
     __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red_s[w][threadIdx.x];
+        ctr_s[threadIdx.x] = t / (double)(n > 0 ? n : 1);
+    }
+    __syncthreads();
+    double r2 = 0.0;
+    for (int a = threadIdx.x; a < n; a += 256) {
+        const double dx = ld3(pos, o + a, 0) - ctr_s[0], dy = ld3(pos, o + a, 1) - ctr_s[1], dz = ld3(pos, o + a, 2) - ctr_s[2];
+        r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, s));
+    __syncthreads();
+    if (lane == 0) red_s[wid][0] = r2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t = fmax(t, red_s[w][0]);
+        const double reach = (sqrt(t) + rc) * (1.0 + 1e-9) + 1e-12;
+        ctr_s[3] = reach * reach;
+    }
+    __syncthreads();
+    const double cx = ctr_s[0], cy = ctr_s[1], cz = ctr_s[2], reach2 = ctr_s[3];
+    // ---- survivors (helpers.py:20-23) and active survivors
     const int total = 27 * n;
     for (int start = 0; start < total; start += 256) {
         const int ip = start + threadIdx.x;
-        bool keep = false;
+        bool keep = false, act = false;
         int a = 0;
         if (ip < total) {
             const int k = ip / n;
@@ -55,91 +85,98 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
             const double px = __dadd_rn(ld3(pos, o + a, 0), shift_of(k % 3, bx));
             const double py = __dadd_rn(ld3(pos, o + a, 1), shift_of((k / 3) % 3, by));
             const double pz = __dadd_rn(ld3(pos, o + a, 2), shift_of(k / 9, bz));
-            const double sx = __ddiv_rn(px, ex), sy = __ddiv_rn(py, ey), sz = __ddiv_rn(pz, ez);
-            const double q = __dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz));
+            const double qx = __ddiv_rn(px, ex), qy = __ddiv_rn(py, ey), qz = __ddiv_rn(pz, ez);
+            const double q = __dadd_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)), __dmul_rn(qz, qz));
             keep = q <= 1.0;
+            const double ux = px - cx, uy = py - cy, uz = pz - cz;
+            act = keep && (ux * ux + uy * uy + uz * uz <= reach2);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[wid] = __popc(bal);
+        const unsigned bal_a = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) { warp_tot[wid] = __popc(bal); warp_act[wid] = __popc(bal_a); }
         __syncthreads();
-        int pre = running_s;
-        for (int w = 0; w < wid; ++w) pre += warp_tot[w];
-        const int rank = pre + __popc(bal & ((1u << lane) - 1u));
+        int pre = running_s, pre_a = running_a;
+        for (int w = 0; w < wid; ++w) { pre += warp_tot[w]; pre_a += warp_act[w]; }
+        const unsigned lt = (1u << lane) - 1u;
+        const int rank = pre + __popc(bal & lt);
         if (ip < total) {
             qrank[base + ip] = keep ? rank : -1;
             if (keep) idmap[base + rank] = a;
+            if (act) active[base + pre_a + __popc(bal_a & lt)] = ip;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < 8; ++w) t += warp_tot[w];
+            int t = 0, ta = 0;
+            for (int w = 0; w < 8; ++w) { t += warp_tot[w]; ta += warp_act[w]; }
             running_s += t;
+            running_a += ta;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) nsurv[m] = running_s;
+    if (threadIdx.x == 0) { nsurv[m] = running_s; nactive[m] = running_a; }
 }
 
-// One warp per (global atom i, image k). FILL=false counts hits, FILL=true writes them.
+// One CTA per molecule, one warp per active image point. FILL=false counts hits, FILL=true writes them.
+// cnt_csr / cnt_ref are zero-initialised by the caller; only active entries are touched.
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, const T* __restrict__ box,
                                                      const float* __restrict__ r_cut,
-                                                     const int* __restrict__ mol_off, const int* __restrict__ atom_mol,
-                                                     int N, const int* __restrict__ qrank,
+                                                     const int* __restrict__ mol_off, const int* __restrict__ qrank,
                                                      const int* __restrict__ idmap, const int* __restrict__ nsurv,
+                                                     const int* __restrict__ active, const int* __restrict__ nactive,
                                                      int* __restrict__ cnt_csr, int* __restrict__ cnt_ref,
                                                      int* __restrict__ row, int* __restrict__ col,
-                                                     int* __restrict__ ref_pos, int* __restrict__ rowptr, int E_cap,
-                                                     int* __restrict__ status) {
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= 27LL * N) return;
-    const int i = (int)(gw / 27), k = (int)(gw - 27LL * i);
-    const int m = atom_mol[i];
-    const int o = mol_off[m], n = mol_off[m + 1] - o, a = i - o;
+                                                     int* __restrict__ ref_pos, int E_cap, int* __restrict__ status) {
+    const int m = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int o = mol_off[m], n = mol_off[m + 1] - o;
     const int64_t base = 27LL * o;
-    const int64_t ip = base + (int64_t)k * n + a;
-    if (FILL && k == 0 && lane == 0) rowptr[i] = cnt_csr[gw];
-    const int q = qrank[ip];
-    if (q < 0) {
-        if (!FILL && lane == 0) { cnt_csr[gw] = 0; cnt_ref[ip] = 0; }
-        return;
-    }
     const double bx = ld3(box, o, 0), by = ld3(box, o, 1), bz = ld3(box, o, 2);
-    const double px = __dadd_rn(ld3(pos, i, 0), shift_of(k % 3, bx));
-    const double py = __dadd_rn(ld3(pos, i, 1), shift_of((k / 3) % 3, by));
-    const double pz = __dadd_rn(ld3(pos, i, 2), shift_of(k / 9, bz));
     const float rcf = r_cut[m];
     const double r_sq = (double)__fmul_rn(rcf, rcf);          // base.py:133, fp32 product (Q9)
-    const int ns = nsurv[m];
-    int running = 0;
-    int out_csr = 0, out_ref = 0;
-    if (FILL) { out_csr = cnt_csr[gw]; out_ref = cnt_ref[ip]; }
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane;
-        bool hit = false;
-        int lab = 0;
-        if (j < n) {
-            const double dx = __dsub_rn(px, ld3(pos, o + j, 0));
-            const double dy = __dsub_rn(py, ld3(pos, o + j, 1));
-            const double dz = __dsub_rn(pz, ld3(pos, o + j, 2));
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (d2 < r_sq) {
-                // base.py:137: the atom column is ALSO indexed through id_mapping (Q6)
-                if (j < ns) lab = idmap[base + j];
-                else { lab = j; atomicOr(status, 2); }        // the reference would raise IndexError here
-                hit = lab != a;                                 // base.py:139 (Q11)
+    const int ns = nsurv[m], na = nactive[m];
+    for (int t = wid; t < na; t += 8) {
+        const int ipl = active[base + t];
+        const int k = ipl / n, a = ipl - k * n;
+        const int i = o + a;
+        const int64_t gw = 27LL * i + k, ip = base + ipl;
+        const double px = __dadd_rn(ld3(pos, i, 0), shift_of(k % 3, bx));
+        const double py = __dadd_rn(ld3(pos, i, 1), shift_of((k / 3) % 3, by));
+        const double pz = __dadd_rn(ld3(pos, i, 2), shift_of(k / 9, bz));
+        int running = 0;
+        int out_csr = 0, out_ref = 0;
+        if (FILL) { out_csr = cnt_csr[gw]; out_ref = cnt_ref[ip]; }
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            int lab = 0;
+            if (j < n) {
+                const double dx = __dsub_rn(px, ld3(pos, o + j, 0));
+                const double dy = __dsub_rn(py, ld3(pos, o + j, 1));
+                const double dz = __dsub_rn(pz, ld3(pos, o + j, 2));
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (d2 < r_sq) {
+                    // base.py:137: the atom column is ALSO indexed through id_mapping (Q6)
+                    if (j < ns) lab = idmap[base + j];
+                    else { lab = j; atomicOr(status, 2); }        // the reference would raise IndexError here
+                    hit = lab != a;                                 // base.py:139 (Q11)
+                }
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const int r = running + __popc(bal & ((1u << lane) - 1u));
+                const int e = out_csr + r;
+                if (e < E_cap) { row[e] = i; col[e] = o + lab; if (ref_pos) ref_pos[e] = out_ref + r; }
+            }
+            running += __popc(bal);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (FILL && hit) {
-            const int r = running + __popc(bal & ((1u << lane) - 1u));
-            const int e = out_csr + r;
-            if (e < E_cap) { row[e] = i; col[e] = o + lab; if (ref_pos) ref_pos[e] = out_ref + r; }
-        }
-        running += __popc(bal);
+        if (!FILL && lane == 0) { cnt_csr[gw] = running; cnt_ref[ip] = running; }
     }
-    if (!FILL && lane == 0) { cnt_csr[gw] = running; cnt_ref[ip] = running; }
+}
+
+__global__ void k_rowptr(const int* __restrict__ cnt_csr, int N, int* __restrict__ rowptr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) rowptr[i] = cnt_csr[27LL * i];
 }
 
 // ---- exclusive scan of two int arrays of equal length (blockIdx.y selects the array) ----
@@ -271,7 +308,7 @@ int64_t enf_edges_workspace_ints(int N) {
     const int64_t n27 = 27LL * N;
     const int64_t nb = (n27 + SCAN_CHUNK - 1) / SCAN_CHUNK;
     // qrank, idmap, cnt_csr(+1), cnt_ref(+1), nsurv(<=N), atom_mol(N), colcnt(N+1), cursor(N), scan sums
-    return 4 * n27 + 2 + 4LL * N + 1 + 2 * nb + 64;
+    return 4 * n27 + 2 + 4LL * N + 1 + 2 * nb + 64 + n27 + N + 4;
 }
 
 template <typename T>
@@ -284,18 +321,20 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     int* cnt_csr = idmap + n27;
     int* cnt_ref = cnt_csr + n27 + 1;
     int* nsurv = cnt_ref + n27 + 1;
-    int* atom_mol = nsurv + N;
+    int* atom_mol = nsurv + N;                // kept for enf_build_col_perm's layout (unused here)
     int* sums = atom_mol + N + (2 * N + 1);   // colcnt/cursor live between (see enf_build_col_perm)
-    enf_count_launch(), k_atom_mol<<<B, 128, 0, st>>>(mol_off, B, atom_mol);
-    enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv);
-    const int64_t warps = n27;
-    const int blocks = (int)((warps * 32 + 255) / 256);
-    enf_count_launch(), k_edges_hits<T, false><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
-                                                   cnt_ref, nullptr, nullptr, nullptr, nullptr, E_cap, status);
+    const int64_t nb_scan = (n27 + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    int* active = sums + 2 * nb_scan + 64;    // 27N
+    int* nactive = active + n27;              // B <= N
+    cudaMemsetAsync(cnt_csr, 0, sizeof(int) * (2 * n27 + 2), st);
+    enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv, active, nactive);
+    enf_count_launch(), k_edges_hits<T, false><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+                                                                  cnt_csr, cnt_ref, nullptr, nullptr, nullptr, E_cap, status);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
-    enf_count_launch(), k_edges_hits<T, true><<<blocks, 256, 0, st>>>(pos, box, r_cut, mol_off, atom_mol, N, qrank, idmap, nsurv, cnt_csr,
-                                                  cnt_ref, row, col, ref_pos, rowptr, E_cap, status);
+    enf_count_launch(), k_edges_hits<T, true><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+                                                                 cnt_csr, cnt_ref, row, col, ref_pos, E_cap, status);
+    enf_count_launch(), k_rowptr<<<(N + 255) / 256, 256, 0, st>>>(cnt_csr, N, rowptr);
     enf_count_launch(), k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
     ENF_CHECK_LAUNCH();
     return ENF_OK;

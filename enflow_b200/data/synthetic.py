@@ -188,3 +188,41 @@ def make_weights(nf, H, L, seed=0, coord_gain=0.5):
             bound = 1.0 / math.sqrt(fan_in)
         sd[name] = _f32(rs.uniform(-bound, bound, size=shape))
     return sd
+
+
+class SYNTHETICDataset:
+    """Dataset plugin following the reference's convention (`enflow/main.py:67-68`: module ``enflow.data.<type>``
+    exporting ``<TYPE>Dataset``): seeded synthetic conformers of one of the BASELINE.json shapes, held in memory as
+    per-molecule ``Data`` objects like ``InMemoryBaseDataset`` (`enflow/data/base.py:250-283`)."""
+
+    def __init__(self, config='c2', num_mols=1024, seed=None, n_atoms=None, ragged=False, **_ignored):
+        import torch
+        from .base import Data
+        kw = {'seed': seed, 'ragged': ragged}
+        if n_atoms:
+            kw['n_atoms'] = int(n_atoms)
+        arrs = make_batch(config, int(num_mols), **kw)
+        self.data_list, o = [], 0
+        for m, n in enumerate(arrs['N']):
+            sl = slice(o, o + int(n))
+            self.data_list.append(Data(z=None, h=torch.tensor(arrs['h'][sl], dtype=torch.float32),
+                                       g=torch.tensor(arrs['g'][sl], dtype=torch.float32),
+                                       pos=torch.tensor(arrs['pos'][sl], dtype=torch.float32),
+                                       vel=torch.tensor(arrs['vel'][sl], dtype=torch.float32), N=int(n),
+                                       r_cut=float(arrs['r_cut'][m]),
+                                       box=torch.tensor(arrs['box'][sl], dtype=torch.float32), label=None))
+            o += int(n)
+
+    def __len__(self):
+        return len(self.data_list)
+
+    def __getitem__(self, idx):
+        return self.data_list[idx]
+
+    @property
+    def node_nf(self):
+        return self.data_list[0].h.shape[1]
+
+    @property
+    def num_atoms_per_mol(self):
+        return self.data_list[0].N

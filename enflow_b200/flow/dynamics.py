@@ -70,9 +70,8 @@ class _FlowFn(torch.autograd.Function):
                                           p(dpos), p(dvel), p(dldj), p(ctx.status), _lib.stream()))
         flow._release_workspace(ctx.ws)
         if flow._dp_group is not None:           # data parallel: one all-reduce over the flat buffer
-            import torch.distributed as dist
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=flow._dp_group)
-            grads.mul_(1.0 / dist.get_world_size(flow._dp_group))
+            from ..parallel import allreduce_mean_
+            allreduce_mean_(grads, flow._dp_group)
         views = flow.grad_views(grads)
         return (None, None, None, None, None, dh, dg, dpos, dvel) + tuple(views)
 
@@ -88,7 +87,7 @@ class LFIntegrator(BaseFlow):
         self.last_status = None
         # edge-MLP arithmetic: 'fp32' (FFMA pipe), 'fp32_tc' (tcgen05, bf16x3 operand split, fp32-accurate),
         # 'bf16' (tcgen05, bf16 operands; the north star's bf16-MLP mode, tolerance 1e-2)
-        self.precision = 'fp32'
+        self.precision = 'fp32_tc'
 
     # ---- workspace: one cached buffer, a fresh one if a pending backward still owns the cached one
     def _take_workspace(self, nbytes, dev, training):

@@ -10,7 +10,7 @@ from enflow_b200.nn.egcl import EGCL
 DEV = 'cuda:0'
 
 
-def build_model(sd, nf, L, H=128, dt=None, precision='fp32'):
+def build_model(sd, nf, L, H=128, dt=None, precision='fp32'):   # the FFMA path is the parity baseline; tc modes are tested explicitly
     from enflow_b200.data import synthetic as syn
     m = LFIntegrator([EGCL(nf, nf, H) for _ in range(L)], ArgMax(nf, H), dt=syn.TRAIN_DT if dt is None else dt)
     m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
