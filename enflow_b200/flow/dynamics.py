@@ -142,9 +142,13 @@ class LFIntegrator(BaseFlow):
             self._edge_caps[(b['B'], b['N'])] = cap
         return out
 
-    def forward(self, data, eps=None):
-        """`dynamics.py:10-23`. ``eps`` (optional) injects the ArgMax noise; default ``torch.randn``."""
-        if eps is None:
+    def forward(self, data, eps=None, dequantize=True):
+        """`dynamics.py:10-23`. ``eps`` (optional) injects the ArgMax noise; default ``torch.randn``.
+        ``dequantize=False`` skips the ArgMax step (h is used as given): the exact inverse of
+        ``reverse(..., quantize=False)``."""
+        if not dequantize:
+            eps = None
+        elif eps is None:
             eps = torch.randn(data.h.size(), device=data.h.device)          # argmax.py:17
         training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         h, g, pos, vel, ldj, ldj_mol, _ = self._run(data, eps, training)

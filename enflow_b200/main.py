@@ -184,11 +184,16 @@ class Main:
         out = self.model.reverse(data)
         np.savetxt(out_prefix + 'h.out', out.h.detach().cpu().numpy(), delimiter=' ')
         write_xyz(out, out_prefix + 'test_out.xyz')
+        # Round-trip self-check.  Upstream compares a tensor with itself (reverse and forward mutate and return
+        # the same Data object, main.py:269-278); here the flow is actually inverted: un-quantised inverse,
+        # then forward without re-dequantising, must give back the latents.
         with torch.no_grad():
-            data_, _ = self.model(out.clone())
-        diff = data_.pos - start.pos.to(data_.pos.dtype)
+            chk = self.model.reverse(start.clone(), quantize=False)
+            back, _ = self.model(chk, dequantize=False)
+        diff = back.pos - start.pos.to(back.pos.dtype)
         box = start.box.to(diff.dtype)
         ok = bool(((diff - (diff / box).round() * box).abs() < 1e-4).all())
+        ok = ok and torch.allclose(back.h, start.h.to(back.h.dtype), atol=1e-4)
         print(ok)
         return out, ok
 
