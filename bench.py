@@ -79,6 +79,10 @@ class ClockSampler:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
         rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
         if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
@@ -210,9 +214,21 @@ def main():
     if E is None:
         E = int(model._edge_caps[(batch, n_atoms)] / 1.25)
 
+    # end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
+    barrier()
+    model.check_status = True          # capacity overflow would be caught (and the step redone) here too
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d = host.to(dev)
+        loss = step(d)
+        loss_host = loss.item()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    model.check_status = False
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)        # let nvidia-smi spin up so samples fall inside the (short) timed region
     L = _lib.lib()
     L.enflow_launch_count(1)
     L.enflow_timing_enable(1)
@@ -229,16 +245,6 @@ def main():
     launches = int(L.enflow_launch_count(1))
     clocks = sampler.stop() if rank == 0 else None
 
-    # end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
-    barrier()
-    model.check_status = True
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        d = host.to(dev)
-        loss = step(d)
-        loss_host = loss.item()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

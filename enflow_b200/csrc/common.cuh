@@ -101,14 +101,15 @@ inline ArgmaxOffsets enf_argmax_offsets(int nf) {
 }
 
 // Per-layer packed (derived) weights, rebuilt once per forward by enflow_pack_weights:
-//   W2T [H][H], W3T [H][H] (k-major rows for the forward GEMMs), W4T [H+nf][H].
+//   W2T [H][H], W3T [H][H] (k-major rows for the forward GEMMs), W4T [H+nf][H], W4A [H][H] = W4[:, nf:].
 struct PackOffsets {
-    int64_t w2t, w3t, w4t, size;
+    int64_t w2t, w3t, w4t, w4a, size;
 };
 inline PackOffsets enf_pack_offsets(int nf) {
     PackOffsets p;
     const int64_t H = ENF_H;
-    p.w2t = 0; p.w3t = H * H; p.w4t = 2 * H * H; p.size = enf_pad(2 * H * H + (H + nf) * H);
+    p.w2t = 0; p.w3t = H * H; p.w4t = 2 * H * H; p.w4a = enf_pad(2 * H * H + (H + nf) * H);
+    p.size = p.w4a + H * H;
     return p;
 }
 

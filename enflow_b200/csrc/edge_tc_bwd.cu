@@ -195,7 +195,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             }
         }
     };
-    auto run_mma = [&](auto&& body) {            // one thread issues, everybody waits for completion
+    auto issue_mma = [&](auto&& body) {          // one thread issues
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -204,10 +204,13 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             body();
             tc::mma_commit(bar_mma);
         }
+    };
+    auto wait_mma = [&]() {                      // everybody waits for completion
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
     };
+    auto run_mma = [&](auto&& body) { issue_mma(body); wait_mma(); };
 
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int e0 = tile * TE;
@@ -283,11 +286,21 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                 store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz3^T image [n][e]
             }
         }
-        // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T
-        run_mma([&]() {
+        // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T   (while the tensor pipe runs: gather dagg, form silu'(z2))
+        issue_mma([&]() {
             issue<SPLIT>(tmem + TW3_COL, 4, zb, ALO, xb, ALO, id_kk128, !first_tile, dT_k, dT_k);
             issue<SPLIT>(tmem + T2_COL, 8, w3, WLO, zb, ALO, id_mm64, false, dW_mn, dT_mn);
         });
+        float da[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const bool ok = ti.valid[ec + j];
+            da[j] = ok ? __ldg(dagg + (int64_t)ti.row[ec + j] * ENF_H + n) : 0.f;
+            const float z = z2r[j];
+            const float sg = tc::sigmoid_sfu(z);
+            z2r[j] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;            // now holds silu'(z2)
+        }
+        wait_mma();
         {
             float v[16];
             tc::tmem_ld16(lane_base + T2_COL + ec, v);
@@ -297,11 +310,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int jj = 8 * ch + j;
-                    const bool ok = ti.valid[ec + jj];
-                    const float da = ok ? __ldg(dagg + (int64_t)ti.row[ec + jj] * ENF_H + n) : 0.f;
-                    const float z = z2r[jj];
-                    const float sg = tc::sigmoid_sfu(z);
-                    const float dz = ok ? (v[jj] + da) * (sg * (1.0f + z * (1.0f - sg))) : 0.f;
+                    const float dz = (v[jj] + da[jj]) * z2r[jj];
                     gb2 += dz;
                     x[j] = dz;
                 }
@@ -309,25 +318,31 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             }
         }
         gen_x1();                                                       // x2^T is dead: rebuild x1 in XB
-        // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T
-        run_mma([&]() {
+        // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   (meanwhile: recompute z1 and silu'(z1) for this thread's edges)
+        issue_mma([&]() {
             issue<SPLIT>(tmem + TW2_COL, 4, zb, ALO, xb, ALO, id_kmn128, !first_tile, dT_k, dX1_mn);
             issue<SPLIT>(tmem + T1_COL, 8, w2, WLO, zb, ALO, id_mm64, false, dW_mn, dT_mn);
         });
         first_tile = false;
+        float ds1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int m = ec + j;
+            const bool ok = ti.valid[m];
+            const float z = ok ? fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) + __ldg(S + (int64_t)ti.col[m] * ENF_H + n)) : 0.f;
+            const float sg = tc::sigmoid_sfu(z);
+            ds1[j] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;
+        }
+        wait_mma();
         {
             float v[16];
             tc::tmem_ld16(lane_base + T1_COL + ec, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int m = ec + j;
-                const bool ok = ti.valid[m];
-                const float r = ti.r[m];
-                const float z = ok ? fmaf(wrn, r, __ldg(P + (int64_t)ti.row[m] * ENF_H + n) + __ldg(S + (int64_t)ti.col[m] * ENF_H + n)) : 0.f;
-                const float sg = tc::sigmoid_sfu(z);
-                const float dz = ok ? v[j] * (sg * (1.0f + z * (1.0f - sg))) : 0.f;
-                if (ok) dz1[(int64_t)(e0 + m) * ENF_H + n] = dz;
-                gwr = fmaf(dz, r, gwr);
+                const float dz = v[j] * ds1[j];
+                if (ti.valid[m]) dz1[(int64_t)(e0 + m) * ENF_H + n] = dz;
+                gwr = fmaf(dz, ti.r[m], gwr);
                 v[j] = wrn * dz;
             }
             const float t = warp_transpose_sum16(v, lane);

@@ -212,7 +212,8 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         // coupling step (dynamics.py:14-21): gradients w.r.t. Q, F, G and the incoming state
         TIMED(TK_COUPLING, enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
         // node_model (egcl.py:65-69)
-        TIMED(TK_NODE_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, w.dagg, dh, lg, w.partial, st));
+        TIMED(TK_NODE_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp,
+                                             w.packed + (int64_t)l * enf_pack_offsets(nf).size, w.dagg, dh, lg, w.partial, st));
         // edge_model + force_model (egcl.py:57-63,71-75); P/S are recomputed, not stored
         TIMED(TK_NODE_PRE, enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
         TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,

@@ -24,7 +24,8 @@ int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const flo
                       float* z4, float* G, cudaStream_t st);
 int64_t enf_node_post_partial_floats(int N, int nf);
 int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const float* dG, int N, int nf,
-                      const float* lp, float* dagg, float* dh, float* lgrad, float* partial, cudaStream_t st);
+                      const float* lp, const float* packed, float* dagg, float* dh, float* lgrad, float* partial,
+                      cudaStream_t st);
 
 int64_t enf_edge_partial_floats();
 int enf_edge_fwd(const int* row, const int* col, const int* E_dev, int E_cap, const float* pos, const float* box,

@@ -133,143 +133,6 @@ __global__ void __launch_bounds__(TPB) k_node_pre_bwd(const float* __restrict__ 
     if (k == 0) p[0] = gb7;
 }
 
-// ------------------------------------------------------------------------------------------ node_post forward
-__global__ void __launch_bounds__(TPB) k_node_post_fwd(const float* __restrict__ h, const float* __restrict__ agg,
-                                                        int N, int nf, const float* __restrict__ W4T,
-                                                        const float* __restrict__ b4, const float* __restrict__ W5,
-                                                        const float* __restrict__ b5, float* __restrict__ z4,
-                                                        float* __restrict__ G) {
-    extern __shared__ float sm[];
-    const int D = nf + ENF_H;
-    float* in = sm;                 // [NT][D]
-    float* x4 = sm + NT * D;        // [NT][H]
-    const int k = threadIdx.x, lane = k & 31, wid = k >> 5;
-    const float bb4 = b4[k];
-    for (int t0 = blockIdx.x * NT; t0 < N; t0 += gridDim.x * NT) {
-        __syncthreads();
-        for (int idx = k; idx < NT * D; idx += TPB) {
-            const int t = idx / D, j = idx % D;
-            float v = 0.f;
-            if (t0 + t < N) v = j < nf ? h[(int64_t)(t0 + t) * nf + j] : agg[(int64_t)(t0 + t) * ENF_H + (j - nf)];
-            in[idx] = v;
-        }
-        __syncthreads();
-        float acc[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = bb4;
-        for (int j = 0; j < D; ++j) {
-            const float w = W4T[(int64_t)j * ENF_H + k];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) acc[t] = fmaf(w, in[t * D + j], acc[t]);
-        }
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            if (t0 + t < N) z4[(int64_t)(t0 + t) * ENF_H + k] = acc[t];
-            x4[t * ENF_H + k] = siluf_(acc[t]);
-        }
-        __syncthreads();
-        // G[t][c] = b5[c] + sum_k W5[c][k] x4[t][k]; warp w takes nodes w, w+4, ...
-        for (int t = wid; t < NT; t += 4) {
-            for (int c = 0; c < nf; ++c) {
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) s = fmaf(W5[c * ENF_H + lane + 32 * q], x4[t * ENF_H + lane + 32 * q], s);
-                s = warp_sum(s);
-                if (lane == 0 && t0 + t < N) G[(int64_t)(t0 + t) * nf + c] = s + b5[c];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------ node_post backward
-// partial layout per CTA: dW4 [(H)*(H+nf)] (native [k][j]) | db4 [H] | dW5 [nf*H] | db5 [nf]
-__global__ void __launch_bounds__(TPB) k_node_post_bwd(const float* __restrict__ h, const float* __restrict__ agg,
-                                                        const float* __restrict__ z4, const float* __restrict__ dG,
-                                                        int N, int nf, const float* __restrict__ W4,
-                                                        const float* __restrict__ W5, float* __restrict__ dagg,
-                                                        float* __restrict__ dh, float* __restrict__ partial) {
-    extern __shared__ float sm[];
-    const int D = nf + ENF_H;
-    float* in = sm;                       // [NT][D]
-    float* dz = in + NT * D;              // [NT][H]
-    float* dgs = dz + NT * ENF_H;         // [NT][MAX_NF]
-    float* gw4 = dgs + NT * ENF_MAX_NF;   // [D][H]  per-CTA accumulator of dW4^T
-    const int k = threadIdx.x;
-    float w5[ENF_MAX_NF], gw5[ENF_MAX_NF];
-#pragma unroll
-    for (int c = 0; c < ENF_MAX_NF; ++c) { w5[c] = c < nf ? W5[c * ENF_H + k] : 0.f; gw5[c] = 0.f; }
-    float gb4 = 0.f;
-    float gb5 = 0.f;   // thread c < nf
-    for (int j = 0; j < D; ++j) gw4[j * ENF_H + k] = 0.f;
-    for (int t0 = blockIdx.x * NT; t0 < N; t0 += gridDim.x * NT) {
-        __syncthreads();
-        for (int idx = k; idx < NT * D; idx += TPB) {
-            const int t = idx / D, j = idx % D;
-            float v = 0.f;
-            if (t0 + t < N) v = j < nf ? h[(int64_t)(t0 + t) * nf + j] : agg[(int64_t)(t0 + t) * ENF_H + (j - nf)];
-            in[idx] = v;
-        }
-        for (int idx = k; idx < NT * ENF_MAX_NF; idx += TPB) {
-            const int t = idx / ENF_MAX_NF, c = idx % ENF_MAX_NF;
-            dgs[idx] = (t0 + t < N && c < nf) ? dG[(int64_t)(t0 + t) * nf + c] : 0.f;
-        }
-        __syncthreads();
-        float dzr[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const float z = (t0 + t < N) ? z4[(int64_t)(t0 + t) * ENF_H + k] : 0.f;
-            const float sg = sigmoidf_(z);
-            const float x = z * sg;
-            float dx = 0.f;
-#pragma unroll
-            for (int c = 0; c < ENF_MAX_NF; ++c) {
-                const float g = dgs[t * ENF_MAX_NF + c];
-                dx = fmaf(w5[c], g, dx);
-                gw5[c] = fmaf(g, x, gw5[c]);
-            }
-            const float d = dx * (sg * (1.0f + z * (1.0f - sg)));
-            dzr[t] = (t0 + t < N) ? d : 0.f;
-            dz[t * ENF_H + k] = dzr[t];
-            gb4 += dzr[t];
-            if (k < nf) gb5 += dgs[t * ENF_MAX_NF + k];
-        }
-        // dW4^T[j][k] += sum_t dz[t][k] * in[t][j]
-        for (int j = 0; j < D; ++j) {
-            float a = gw4[j * ENF_H + k];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) a = fmaf(dzr[t], in[t * D + j], a);
-            gw4[j * ENF_H + k] = a;
-        }
-        __syncthreads();
-        // din[t][j] = sum_k W4[k][j] dz[t][k]; thread j (coalesced over j in the native layout)
-        for (int j = k; j < D; j += TPB) {
-            float a[NT];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) a[t] = 0.f;
-            for (int kk = 0; kk < ENF_H; ++kk) {
-                const float w = W4[(int64_t)kk * D + j];
-#pragma unroll
-                for (int t = 0; t < NT; ++t) a[t] = fmaf(w, dz[t * ENF_H + kk], a[t]);
-            }
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                if (t0 + t < N) {
-                    if (j < nf) dh[(int64_t)(t0 + t) * nf + j] += a[t];
-                    else dagg[(int64_t)(t0 + t) * ENF_H + (j - nf)] = a[t];
-                }
-            }
-        }
-    }
-    __syncthreads();
-    float* p = partial + (int64_t)blockIdx.x * ((int64_t)ENF_H * D + ENF_H + nf * ENF_H + nf);
-    for (int j = 0; j < D; ++j) p[(int64_t)k * D + j] = gw4[j * ENF_H + k];
-    p += (int64_t)ENF_H * D;
-    p[k] = gb4; p += ENF_H;
-    for (int c = 0; c < nf; ++c) p[c * ENF_H + k] = gw5[c];
-    p += nf * ENF_H;
-    if (k < nf) p[k] = gb5;
-}
-
 // ------------------------------------------------------------------------------------------ partial reduce
 struct SegTable {
     int n;
@@ -290,13 +153,14 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int n_cta, 
 
 __global__ void k_transpose_pack(const float* __restrict__ W2, const float* __restrict__ W3,
                                  const float* __restrict__ W4, int nf, float* __restrict__ W2T,
-                                 float* __restrict__ W3T, float* __restrict__ W4T) {
+                                 float* __restrict__ W3T, float* __restrict__ W4T, float* __restrict__ W4A) {
     const int D = nf + ENF_H;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < ENF_H * ENF_H) {
         const int k = idx / ENF_H, n = idx % ENF_H;     // out[k][n] = W[n][k]
         W2T[idx] = W2[n * ENF_H + k];
         W3T[idx] = W3[n * ENF_H + k];
+        W4A[idx] = W4[(int64_t)k * D + nf + n];         // W4A[k][jj] = W4[k][nf + jj] (aligned rows)
     }
     if (idx < D * ENF_H) {
         const int j = idx / ENF_H, k = idx % ENF_H;     // W4T[j][k] = W4[k][j]
@@ -318,7 +182,7 @@ int enf_pack_layer(const float* layer_params, int nf, float* packed, cudaStream_
     const int total = (nf + ENF_H) * ENF_H;
     enf_count_launch(), k_transpose_pack<<<(total + 255) / 256, 256, 0, st>>>(layer_params + o.off[P_W2], layer_params + o.off[P_W3],
                                                           layer_params + o.off[P_W4], nf, packed + p.w2t,
-                                                          packed + p.w3t, packed + p.w4t);
+                                                          packed + p.w3t, packed + p.w4t, packed + p.w4a);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -356,52 +220,3 @@ int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float
     return ENF_OK;
 }
 
-static size_t node_post_fwd_smem(int nf) { return sizeof(float) * (NT * (nf + ENF_H) + NT * ENF_H); }
-static size_t node_post_bwd_smem(int nf) {
-    return sizeof(float) * (NT * (nf + ENF_H) + NT * ENF_H + NT * ENF_MAX_NF + (nf + ENF_H) * ENF_H);
-}
-
-int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* lp, const float* packed,
-                      float* z4, float* G, cudaStream_t st) {
-    if (N == 0) return ENF_OK;
-    const EgclOffsets o = enf_egcl_offsets(nf);
-    const PackOffsets p = enf_pack_offsets(nf);
-    enf_count_launch(), k_node_post_fwd<<<enf_node_grid(N), TPB, node_post_fwd_smem(nf), st>>>(
-        h, agg, N, nf, packed + p.w4t, lp + o.off[P_B4], lp + o.off[P_W5], lp + o.off[P_B5], z4, G);
-    ENF_CHECK_LAUNCH();
-    return ENF_OK;
-}
-
-int enf_node_post_grid_bwd(int N) {
-    int tiles = (N + NT - 1) / NT;
-    int cap = enf_num_sms() * 2;
-    return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
-}
-
-int64_t enf_node_post_partial_floats(int N, int nf) {
-    return (int64_t)enf_node_post_grid_bwd(N) * ((int64_t)ENF_H * (nf + ENF_H) + ENF_H + nf * ENF_H + nf);
-}
-
-int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const float* dG, int N, int nf,
-                      const float* lp, float* dagg, float* dh, float* lgrad, float* partial, cudaStream_t st) {
-    if (N == 0) return ENF_OK;
-    const EgclOffsets o = enf_egcl_offsets(nf);
-    const int grid = enf_node_post_grid_bwd(N);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_node_post_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
-    enf_count_launch(), k_node_post_bwd<<<grid, TPB, node_post_bwd_smem(nf), st>>>(h, agg, z4, dG, N, nf, lp + o.off[P_W4],
-                                                               lp + o.off[P_W5], dagg, dh, partial);
-    SegTable s;
-    const int D = nf + ENF_H;
-    const int lens[4] = {ENF_H * D, ENF_H, nf * ENF_H, nf};
-    const int dsts[4] = {(int)o.off[P_W4], (int)o.off[P_B4], (int)o.off[P_W5], (int)o.off[P_B5]};
-    int src = 0;
-    s.n = 4;
-    for (int i = 0; i < 4; ++i) { s.src[i] = src; s.dst[i] = dsts[i]; s.len[i] = lens[i]; src += lens[i]; }
-    enf_count_launch(), k_reduce_partials<<<(src + 255) / 256, 256, 0, st>>>(partial, grid, src, s, lgrad);
-    ENF_CHECK_LAUNCH();
-    return ENF_OK;
-}
