@@ -33,6 +33,8 @@ CONFIGS = {
     'c1': ('c1', 64, {}, 4, 'example/train.yaml shape: 22-atom conformers, radius graph, batch 64'),
     'c2': ('c2', 1024, {'n_atoms': 29}, 5, 'QM9-sized synthetic molecules, 29 atoms fully connected, batch 1024 per GPU'),
     'c3': ('c3', 1024, {}, 1, 'LJ-55 clusters, 55 particles fully connected, batch 1024 per GPU'),
+    'c4': ('c4', 16384, {}, 4, 'example/generate.yaml inverse pass: 22-atom latents, 16384 conformers per launch per GPU, '
+                               'state + per-molecule log-det out'),
     'c5': ('c5', 32, {'n_atoms': 500}, 5, '500-atom fragments, radius-cutoff graph, batch 32 per GPU'),
 }
 
@@ -104,7 +106,11 @@ def cpu_port_throughput(config, nf, sample_mols, steps, warmup, kwargs):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.train_step(sd, L_LAYERS, arrs, syn.TRAIN_DT, eps, syn.TRAIN_KBT, syn.TRAIN_SOFTENING)
+        if config == 'c4':
+            with torch.no_grad():
+                orc.lf_reverse(orc.params_to_torch(sd), L_LAYERS, orc.to_torch(arrs), syn.TRAIN_DT)
+        else:
+            orc.train_step(sd, L_LAYERS, arrs, syn.TRAIN_DT, eps, syn.TRAIN_KBT, syn.TRAIN_SOFTENING)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return sample_mols / (sum(times) / len(times)), torch.get_num_threads(), sum(times) / len(times)
@@ -117,7 +123,7 @@ def run_reference(args):
     if rank != 0:
         return
     config, batch, kwargs, nf, desc = CONFIGS[args.config]
-    sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c5': 1}[args.config]
+    sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c4': 256, 'c5': 1}[args.config]
     mols_s, cores, sec = cpu_port_throughput(config, nf, sample, args.steps, min(args.warmup, 1), kwargs)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': mols_s, 'unit': UNIT, 'n_gpus': args.gpus,
@@ -178,7 +184,7 @@ def main():
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
     # per-rank synthetic batch (weak scaling: fixed per-GPU batch), pinned host copy + resident device copy
-    arrs = syn.make_batch(config, batch, seed=1234 + 10 * rank + {'c1': 1, 'c2': 2, 'c3': 3, 'c5': 5}[config], **kwargs)
+    arrs = syn.make_batch(config, batch, seed=1234 + 10 * rank + {'c1': 1, 'c2': 2, 'c3': 3, 'c4': 4, 'c5': 5}[config], **kwargs)
     f32 = lambda k: torch.tensor(arrs[k], dtype=torch.float32)
     host = Data(h=f32('h'), g=f32('g'), pos=f32('pos'), vel=f32('vel'), N=torch.tensor(arrs['N']),
                 r_cut=torch.tensor(arrs['r_cut']), box=f32('box')).pin_memory()
@@ -193,7 +199,12 @@ def main():
         v._meta = d._meta
         return v
 
+    generate = config == 'c4'
+
     def step(d):
+        if generate:                                          # dynamics.py:25-37 + per-molecule -sum(Q)
+            out = model.reverse(d)
+            return out.neg_ldj_mol.sum()
         opt.zero_grad(set_to_none=True)
         out, ldj = model(d)                                   # eps drawn with torch.randn like argmax.py:17
         loss = nll(out, ldj)
@@ -217,13 +228,21 @@ def main():
     # end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
     barrier()
     model.check_status = True          # capacity overflow would be caught (and the step redone) here too
+    for _ in range(args.warmup):       # warm the host-buffer path too (allocator growth for the per-step device batch)
+        step(host.to(dev)).item()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         d = host.to(dev)
         loss = step(d)
         loss_host = loss.item()
+        e2e_steps.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get('ENFLOW_BENCH_DEBUG'):
+        print('e2e per-step ms:', [round(1e3 * x, 2) for x in e2e_steps], file=sys.stderr)
     model.check_status = False
     sampler = ClockSampler(local)
     if rank == 0:
@@ -262,11 +281,22 @@ def main():
         roof = None
         if dom in flops and avg[dom] > 0:
             ach = flops[dom] / (avg[dom] * 1e-3) / 1e12
-            roof = {'kernel': 'k_' + dom, 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'],
-                    'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'], 'traffic': None,
-                    'peak_source': pk['source'] + ' bf16 dense sustained',
-                    'note': 'fp32 mode: the dense layers run on the FFMA pipe (1xTF32 misses the 1e-5 parity budget); '
-                            'fraction is quoted against the tensor-pipe peak the bf16 path will use'}
+            tc_mode = args.precision != 'fp32'
+            kname = 'k_' + dom + ('_tc' if tc_mode else '')
+            # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
+            # (profiles/r1_edge_bwd_tc_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
+            traffic = {'k_edge_bwd_tc': 459.4e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
+            mma_per_gemm = {'fp32': 0, 'fp32_tc': 3, 'bf16': 1}[args.precision]
+            roof = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'],
+                    'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
+                    'peak_source': pk['source'] + ' bf16 dense sustained (kernel timed inside a long step)',
+                    'algorithmic_flops_per_launch': flops[dom],
+                    'note': ('achieved = algorithmic FLOPs (2x forward: dgrad + wgrad of the two HxH layers) / CUDA-event time. '
+                             f'The tensor pipe executes {mma_per_gemm} bf16 MMA(s) per GEMM term (bf16x3 operand split keeps fp32 '
+                             'parity) and 6 GEMMs per tile (2 recompute + 2 dgrad + 2 wgrad), i.e. '
+                             f'{mma_per_gemm * 1.5:.1f}x the algorithmic FLOPs; the kernel is bound by the SiLU/split epilogues '
+                             '(XU + FMA pipes), see DESIGN.md section 4') if tc_mode else
+                            'fp32 FFMA baseline path: dense layers on the CUDA cores'}
         seg_bytes = E * H * 4 + (n_atoms + 1) * 4 + n_atoms * H * 4
         cpl_bytes = n_atoms * (19 + 5 * nf) * 4 + batch * 4
         hbm = {}
@@ -284,8 +314,9 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': desc, 'per_gpu_batch': batch, 'global_batch': mols, 'atoms_per_gpu': n_atoms,
                        'edges_per_layer_per_gpu': E, 'layers': L_LAYERS, 'hidden': H, 'nf': nf, 'edge_mlp': args.precision,
-                       'step': 'forward + Alchemical_NLL + backward (all parameter grads)'
-                               + (' + NCCL all-reduce of the flat gradient buffer' if world > 1 else '') + ' + Adam',
+                       'step': ('LFIntegrator.reverse (inverse pass, no collective)' if generate else
+                                'forward + Alchemical_NLL + backward (all parameter grads)'
+                                + (' + NCCL all-reduce of the flat gradient buffer' if world > 1 else '') + ' + Adam'),
                        'parallelism': f'dp{world}', 'l2': 'no explicit flush: every step streams the saved edge '
                        'activations (2*L*E*H*4 bytes, far above the 126 MB L2) through HBM'},
             'clocks': clocks,
@@ -298,7 +329,7 @@ def main():
             'kernel_share_of_step': share,
         }
         if world == 1 and not args.no_cpu_baseline:
-            sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c5': 1}[args.config]
+            sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c4': 256, 'c5': 1}[args.config]
             mols_s, cores, sec = cpu_port_throughput(config, nf, sample, 2, 1, kwargs)
             line['cpu_baseline'] = {'value': mols_s, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': f'{sample} molecules of the same config per step, fp64 torch CPU port '

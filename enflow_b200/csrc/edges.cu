@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, c
     const float rcf = r_cut[m];
     const double r_sq = (double)__fmul_rn(rcf, rcf);          // base.py:133, fp32 product (Q9)
     const int ns = nsurv[m], na = nactive[m];
-    for (int t = wid; t < na; t += 8) {
+    for (int t = wid + 8 * blockIdx.y; t < na; t += 8 * gridDim.y) {     // gridDim.y CTAs share a large molecule
         const int ipl = active[base + t];
         const int k = ipl / n, a = ipl - k * n;
         const int i = o + a;
@@ -328,11 +328,15 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     int* nactive = active + n27;              // B <= N
     cudaMemsetAsync(cnt_csr, 0, sizeof(int) * (2 * n27 + 2), st);
     enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv, active, nactive);
-    enf_count_launch(), k_edges_hits<T, false><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+    // large molecules: several CTAs per molecule (the active list of a 500-atom fragment has ~3000 entries)
+    int ysplit = (B > 0 ? N / B : 1) / 24;
+    ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
+    const dim3 hgrid(B, ysplit);
+    enf_count_launch(), k_edges_hits<T, false><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
                                                                   cnt_csr, cnt_ref, nullptr, nullptr, nullptr, E_cap, status);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
-    enf_count_launch(), k_edges_hits<T, true><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+    enf_count_launch(), k_edges_hits<T, true><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
                                                                  cnt_csr, cnt_ref, row, col, ref_pos, E_cap, status);
     enf_count_launch(), k_rowptr<<<(N + 255) / 256, 256, 0, st>>>(cnt_csr, N, rowptr);
     enf_count_launch(), k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);

@@ -12,7 +12,8 @@ sd=syn.make_weights(nf,H,L)
 model=LFIntegrator([EGCL(nf,nf,H) for _ in range(L)],ArgMax(nf,H),dt=syn.TRAIN_DT)
 model.load_state_dict({k:torch.tensor(v) for k,v in sd.items()}); model=model.to(dev)
 nll=Alchemical_NLL(kBT=syn.TRAIN_KBT,softening=0.1); opt=torch.optim.Adam(model.parameters(),lr=1e-3)
-arrs=syn.make_batch('c2',1024,n_atoms=29)
+cfg=sys.argv[1] if len(sys.argv)>1 else 'c2'
+arrs=syn.make_batch('c2',1024,n_atoms=29) if cfg=='c2' else syn.make_batch('c5',32,n_atoms=500)
 f32=lambda k: torch.tensor(arrs[k],dtype=torch.float32)
 host=Data(h=f32('h'),g=f32('g'),pos=f32('pos'),vel=f32('vel'),N=torch.tensor(arrs['N']),r_cut=torch.tensor(arrs['r_cut']),box=f32('box')).pin_memory()
 def T(): torch.cuda.synchronize(); return time.perf_counter()
