@@ -42,7 +42,11 @@ SIGNATURES = {
     'enflow_edge_fwd': (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     'enflow_tc_pack_bytes': (i64, []),
     'enflow_tc_pack_layer': (i32, [vp, i32, vp, vp]),
-    'enflow_edge_fwd_tc': (i32, [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'enflow_edge_fwd_tc': (i32, [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    'enflow_run_rows': (i64, [i32, i32]),
+    'enflow_run_scratch_ints': (i64, [i32]),
+    'enflow_run_index': (i32, [vp, i32, vp, vp, vp]),
+    'enflow_run_sum128': (i32, [vp, vp, vp, i32, i32, vp, vp]),
     'enflow_node_post_fwd': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp]),
     'enflow_coupling_fwd': (i32, [vp] * 9 + [i32, i32, f32] + [vp] * 6),
     'enflow_coupling_bwd': (i32, [vp, vp, vp, i32, i32, f32] + [vp] * 8),

@@ -145,11 +145,19 @@ int enflow_tc_pack_layer(const float* lp, int nf, void* img, void* stream) {
 }
 int enflow_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
                        const float* box, const float* P, const float* S, const float* lp, const void* wimg, int nf,
-                       float* z2, float* z3, float* s, float* trans, void* stream) {
+                       const int* rowptr, const int* mis, float* runs, float* s, float* trans, void* stream) {
     ENF_CHECK_ARG(mode == 1 || mode == 2, "edge_fwd_tc: mode must be 1 (split) or 2 (bf16)");
     ENF_CHECK_ARG((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "edge_fwd_tc: weight image must be 16-byte aligned");
-    return enf_edge_fwd_tc(mode, row, col, E_dev, E_cap, pos, box, P, S, lp, (const unsigned char*)wimg, nf, z2, z3, s,
-                           trans, ST(stream));
+    return enf_edge_fwd_tc(mode, row, col, E_dev, E_cap, pos, box, P, S, lp, (const unsigned char*)wimg, nf, rowptr, mis,
+                           runs, s, trans, ST(stream));
+}
+int64_t enflow_run_rows(int E_cap, int N) { return enf_run_rows(E_cap, N); }
+int64_t enflow_run_scratch_ints(int N) { return enf_scan_scratch_ints(N + 2); }
+int enflow_run_index(const int* rowptr, int N, int* mis, int* scratch, void* stream) {
+    return enf_run_index(rowptr, N, mis, scratch, ST(stream));
+}
+int enflow_run_sum128(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out, void* stream) {
+    return enf_run_sum128(runs, rowptr, mis, N, E_cap, out, ST(stream));
 }
 int enflow_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* lp, const float* packed,
                          float* z4, float* G, void* stream) {

@@ -22,7 +22,7 @@ namespace {
 constexpr int THREADS = 512;
 
 struct TileInfo {
-    int row[tc::TILE], col[tc::TILE], valid[tc::TILE];
+    int row[tc::TILE], col[tc::TILE], valid[tc::TILE], start[tc::TILE], mis[tc::TILE];
     float d[tc::TILE][3];
     float r[tc::TILE];
     float s_part[4][tc::TILE];
@@ -124,7 +124,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
               const float* __restrict__ pos, const float* __restrict__ box, const float* __restrict__ P,
               const float* __restrict__ S, const float* __restrict__ W1, int e1, const float* __restrict__ b2,
               const float* __restrict__ b3, const float* __restrict__ wc, const unsigned char* __restrict__ wimg,
-              float* __restrict__ z2, float* __restrict__ z3, float* __restrict__ s_out, float* __restrict__ trans) {
+              const int* __restrict__ rowptr, const int* __restrict__ mis, float* __restrict__ runs,
+              float* __restrict__ s_out, float* __restrict__ trans) {
     using L = Smem<SPLIT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
@@ -187,6 +188,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                 d2 = wrapf_(pos[(int64_t)i * 3 + 2] - pos[(int64_t)j * 3 + 2], 0.5f * box[(int64_t)i * 3 + 2]);
             }
             ti.row[tid] = i; ti.col[tid] = j; ti.valid[tid] = ok;
+            ti.start[tid] = ok && (e == rowptr[i]);
+            ti.mis[tid] = ok ? mis[i + 1] : 0;
             ti.d[tid][0] = d0; ti.d[tid][1] = d1; ti.d[tid][2] = d2;
             ti.r[tid] = d0 * d0 + d1 * d1 + d2 * d2;
         }
@@ -225,16 +228,34 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
-        // ---- epilogue 1: bias, save z2 (coalesced: lanes = consecutive n), x2^T = silu(z2)^T as the next operand
+        // ---- epilogue 1: bias, x2^T = silu(z2)^T as the next operand, and the segment sums of x2 over each
+        //      row (egcl.py:66) as per-run partials: this thread owns hidden unit n for 32 consecutive edges, so
+        //      the sum over a row's edges is a thread-local running sum flushed at row starts (see segment.cu)
         {
             float v[32];
             tc::tmem_ld32(taddr, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 v[j] += b2n;
-                const bool ok = ti.valid[ec + j];
-                if (ok) z2[(int64_t)(e0 + ec + j) * ENF_H + n] = v[j];
-                v[j] = ok ? v[j] * tc::sigmoid_sfu(v[j]) : 0.f;
+                v[j] = ti.valid[ec + j] ? v[j] * tc::sigmoid_sfu(v[j]) : 0.f;
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int jb = 16 * half;
+                if (ti.valid[ec + jb]) {
+                    int rid = ((e0 + ec + jb) >> 4) + ti.mis[ec + jb];
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j > 0 && ti.start[ec + jb + j]) {
+                            runs[(int64_t)rid * ENF_H + n] = acc;
+                            ++rid;
+                            acc = 0.f;
+                        }
+                        acc += v[jb + j];
+                    }
+                    runs[(int64_t)rid * ENF_H + n] = acc;
+                }
             }
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
@@ -255,14 +276,13 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
-        // ---- epilogue 2: bias, save z3, s[e] = sum_n wc[n] silu(z3[e][n]) (transpose-reduce over the warp's 32 n)
+        // ---- epilogue 2: bias, s[e] = sum_n wc[n] silu(z3[e][n]) (transpose-reduce over the warp's 32 n)
         {
             float v[32];
             tc::tmem_ld32(taddr, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 v[j] += b3n;
-                if (ti.valid[ec + j]) z3[(int64_t)(e0 + ec + j) * ENF_H + n] = v[j];
                 v[j] = wcn * (v[j] * tc::sigmoid_sfu(v[j]));
             }
             ti.s_part[q][ec + lane] = warp_transpose_sum(v, lane);
@@ -297,7 +317,8 @@ int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t 
 // mode 1 = split (fp32-accurate), mode 2 = bf16
 int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
                     const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
-                    int nf, float* z2, float* z3, float* s_out, float* trans, cudaStream_t st) {
+                    int nf, const int* rowptr, const int* mis, float* runs, float* s_out, float* trans,
+                    cudaStream_t st) {
     if (E_cap == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     int grid = (E_cap + tc::TILE - 1) / tc::TILE;
@@ -311,11 +332,11 @@ int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, 
     if (mode == 1)
         enf_count_launch(), k_edge_fwd_tc<true><<<grid, THREADS, Smem<true>::total, st>>>(
             row, col, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
-            lp + o.off[P_WC], wimg, z2, z3, s_out, trans);
+            lp + o.off[P_WC], wimg, rowptr, mis, runs, s_out, trans);
     else
         enf_count_launch(), k_edge_fwd_tc<false><<<grid, THREADS, Smem<false>::total, st>>>(
             row, col, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
-            lp + o.off[P_WC], wimg, z2, z3, s_out, trans);
+            lp + o.off[P_WC], wimg, rowptr, mis, runs, s_out, trans);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

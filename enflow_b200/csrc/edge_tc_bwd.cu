@@ -26,7 +26,7 @@ constexpr int X1_BLK = TE * 128;           // block stride of the [e][k] image
 constexpr uint32_t T1_COL = 0, T2_COL = 64, TW2_COL = 128, TW3_COL = 256, TMEM_COLS = 512;
 
 struct TileInfoB {
-    int row[TE], col[TE], valid[TE];
+    int row[TE], col[TE], valid[TE], start[TE], mis[TE];
     float d[TE][3], r[TE], ds[TE], ddir[TE][3];
     float dr_part[4][TE];
 };
@@ -108,7 +108,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
               const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ wc,
               const unsigned char* __restrict__ wimg, const float* __restrict__ s_saved,
               const float* __restrict__ dagg, const float* __restrict__ dF, float coords_weight,
-              float* __restrict__ dz1, float* __restrict__ dd_out, float* __restrict__ partial) {
+              const int* __restrict__ mis, float* __restrict__ runs, float* __restrict__ dz1,
+              float* __restrict__ dd_out, float* __restrict__ partial) {
     using L = SmemB<SPLIT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
@@ -240,6 +241,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                 q0 = dtr[0] * s; q1 = dtr[1] * s; q2 = dtr[2] * s;
             }
             ti.row[tid] = i; ti.col[tid] = j; ti.valid[tid] = ok;
+            ti.start[tid] = ok && (e == rowptr[i]);
+            ti.mis[tid] = ok ? mis[i + 1] : 0;
             ti.d[tid][0] = d0; ti.d[tid][1] = d1; ti.d[tid][2] = d2;
             ti.r[tid] = d0 * d0 + d1 * d1 + d2 * d2;
             ti.ds[tid] = ds;
@@ -337,14 +340,26 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         {
             float v[16];
             tc::tmem_ld16(lane_base + T1_COL + ec, v);
+            // dz1 = dx1 * silu'(z1): stored per edge (for the column-grouped sum dS) and reduced over each row's
+            // edges into per-run partials (dP, see segment.cu) by a thread-local running sum
+            int rid = ((e0 + ec) >> 4) + ti.mis[ec];
+            float acc = 0.f;
+            const bool any = ti.valid[ec];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int m = ec + j;
                 const float dz = v[j] * ds1[j];
                 if (ti.valid[m]) dz1[(int64_t)(e0 + m) * ENF_H + n] = dz;
+                if (j > 0 && ti.start[m]) {
+                    runs[(int64_t)rid * ENF_H + n] = acc;
+                    ++rid;
+                    acc = 0.f;
+                }
+                acc += dz;
                 gwr = fmaf(dz, ti.r[m], gwr);
                 v[j] = wrn * dz;
             }
+            if (any) runs[(int64_t)rid * ENF_H + n] = acc;
             const float t = warp_transpose_sum16(v, lane);
             if (lane < 16) ti.dr_part[q][ec + lane] = t;
         }
@@ -398,7 +413,8 @@ int enf_edge_reduce_partials(const float* partial, int n_cta, float* lgrad, int 
 int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
                     const float* pos, const float* box, const float* P, const float* S, const float* lp,
                     const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
-                    float coords_weight, float* dz1, float* dd, float* lgrad, float* partial, cudaStream_t st) {
+                    float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
+                    float* partial, cudaStream_t st) {
     if (E_cap == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const int grid = enf_num_sms();
@@ -411,11 +427,11 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
     if (mode == 1)
         enf_count_launch(), k_edge_bwd_tc<true><<<grid, THREADS, SmemB<true>::total, st>>>(
             row, col, rowptr, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
-            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, dz1, dd, partial);
+            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, mis, runs, dz1, dd, partial);
     else
         enf_count_launch(), k_edge_bwd_tc<false><<<grid, THREADS, SmemB<false>::total, st>>>(
             row, col, rowptr, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
-            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, dz1, dd, partial);
+            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, mis, runs, dz1, dd, partial);
     ENF_CHECK_LAUNCH();
     return enf_edge_reduce_partials(partial, grid, lgrad, nf, st);
 }

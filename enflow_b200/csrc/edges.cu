@@ -296,9 +296,10 @@ __global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, c
 
 static int scan2(int* a0, int* a1, int64_t n, int* sums, cudaStream_t st) {
     const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    dim3 g(nb, 2);
+    const int ny = a1 ? 2 : 1;
+    dim3 g(nb, ny);
     enf_count_launch(), k_scan_sums<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
-    enf_count_launch(), k_scan_top<<<dim3(1, 2), SCAN_THREADS, 0, st>>>(sums, nb);
+    enf_count_launch(), k_scan_top<<<dim3(1, ny), SCAN_THREADS, 0, st>>>(sums, nb);
     enf_count_launch(), k_scan_apply<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
@@ -367,3 +368,7 @@ int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, in
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
+
+// in-place exclusive scan of a[0..n); a[n] receives the total. sums: >= ceil(n/2048) ints of scratch
+int64_t enf_scan_scratch_ints(int64_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 8; }
+int enf_scan_int(int* a, int64_t n, int* sums, cudaStream_t st) { return scan2(a, nullptr, n, sums, st); }

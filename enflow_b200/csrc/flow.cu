@@ -33,8 +33,8 @@ struct Bump {
 };
 
 struct LayerSave {           // kept per layer when training
-    int *row, *col, *rowptr, *E_dev;
-    float *Q, *z2, *z3, *s, *agg, *z4;
+    int *row, *col, *rowptr, *E_dev, *mis;
+    float *Q, *z2, *z3, *s, *agg, *z4;     // z2/z3 only in mode 0 (the tensor-core backward recomputes them)
 };
 
 struct Workspace {
@@ -43,7 +43,8 @@ struct Workspace {
     LayerSave layer[16];
     float* packed;           // L * pack size
     unsigned char* tcimg;    // L * swizzled bf16 weight images for the tcgen05 kernels
-    float *P, *S, *F, *G, *trans, *wr;
+    float *P, *S, *F, *G, *trans, *wr, *runs;
+    int* run_scratch;
     int* edges_ws;
     float* logq_atom;
     double* logq_mol;
@@ -78,7 +79,10 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
     for (int l = 0; l < saved_layers; ++l) {
         LayerSave& s = w.layer[l];
         s.row = b.take<int>(E); s.col = b.take<int>(E); s.rowptr = b.take<int>(N + 1); s.E_dev = b.take<int>(2);
-        s.Q = b.take<float>(N); s.z2 = b.take<float>(E * H); s.z3 = b.take<float>(E * H); s.s = b.take<float>(E);
+        s.mis = b.take<int>(N + 2);
+        s.Q = b.take<float>(N); s.s = b.take<float>(E);
+        s.z2 = d.mode == 0 ? b.take<float>(E * H) : nullptr;
+        s.z3 = d.mode == 0 ? b.take<float>(E * H) : nullptr;
         s.agg = b.take<float>(N * H); s.z4 = b.take<float>(N * H);
     }
     w.packed = b.take<float>((size_t)d.L * enf_pack_offsets(d.nf).size);
@@ -86,6 +90,8 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
     w.P = b.take<float>(N * H); w.S = b.take<float>(N * H);
     w.F = b.take<float>(N * 3); w.G = b.take<float>(N * nf);
     w.trans = b.take<float>(E * 3); w.wr = b.take<float>(H);
+    w.runs = d.mode ? b.take<float>((size_t)enf_run_rows(d.E_cap, d.N) * H) : nullptr;
+    w.run_scratch = b.take<int>((size_t)enf_scan_scratch_ints(d.N + 2));
     w.edges_ws = b.take<int>((size_t)enf_edges_workspace_ints(d.N));
     w.logq_atom = b.take<float>(N); w.logq_mol = b.take<double>(d.B); w.log_q = b.take<float>(1);
     if (training) {
@@ -130,13 +136,17 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
     TIMED(TK_EDGES, enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
                                      sv.E_dev, status, w.edges_ws, st));
     TIMED(TK_NODE_PRE, enf_node_pre_fwd(h, d.N, d.nf, lp, w.P, w.S, sv.Q, st));
-    if (d.mode == 0)
+    if (d.mode == 0) {
         TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr,
                                         sv.z2, sv.z3, sv.s, w.trans, st));
-    else
+        TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
+    } else {
+        // tensor-core path: the kernel reduces silu(z2) over each row into per-run partials; no [E,H] store
+        ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
         TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, tcimg, d.nf,
-                                           sv.z2, sv.z3, sv.s, w.trans, st));
-    TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
+                                           sv.rowptr, sv.mis, w.runs, sv.s, w.trans, st));
+        TIMED(TK_SEG128, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, sv.agg, st));
+    }
     TIMED(TK_SEG3, enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
     TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
     return ENF_OK;
@@ -218,15 +228,17 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         TIMED(TK_NODE_PRE, enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
         TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
                                    w.edges_ws, st));
-        if (d.mode == 0)
+        if (d.mode == 0) {
             TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf,
                                             w.wr, sv.z2, sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg,
                                             w.partial, st));
-        else
+            TIMED(TK_SEG128, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
+        } else {
             TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P,
-                                               w.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1,
-                                               w.dd, lg, w.partial, st));
-        TIMED(TK_SEG128, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
+                                               w.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
+                                               w.runs, w.dz1, w.dd, lg, w.partial, st));
+            TIMED(TK_SEG128, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, st));
+        }
         TIMED(TK_SEG128, enf_segment_sum128(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, st));
         // coord_diff = pos[row] - pos[col] (data/base.py:17): +dd onto row atoms, -dd onto col atoms
         TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));

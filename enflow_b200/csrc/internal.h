@@ -66,8 +66,15 @@ int64_t enf_tc_pack_bytes();
 int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t st);
 int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
                     const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
-                    int nf, float* z2, float* z3, float* s_out, float* trans, cudaStream_t st);
+                    int nf, const int* rowptr, const int* mis, float* runs, float* s_out, float* trans,
+                    cudaStream_t st);
 int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
                     const float* pos, const float* box, const float* P, const float* S, const float* lp,
                     const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
-                    float coords_weight, float* dz1, float* dd, float* lgrad, float* partial, cudaStream_t st);
+                    float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
+                    float* partial, cudaStream_t st);
+// per-run partial segment sums (segment.cu): mis = N+2 ints, runs = enf_run_rows(E_cap, N) x 128 floats
+int64_t enf_scan_scratch_ints(int64_t n);
+int enf_run_index(const int* rowptr, int N, int* mis, int* scratch, cudaStream_t st);
+int enf_run_sum128(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out, cudaStream_t st);
+inline int64_t enf_run_rows(int E_cap, int N) { return (int64_t)E_cap / 16 + N + 2; }

@@ -76,7 +76,57 @@ __global__ void __launch_bounds__(256) k_segment_sum3(const float* __restrict__ 
     }
 }
 
+// ---- "runs": partial segment sums produced inside the tensor-core edge kernels ---------------------------
+// A run is a maximal stretch of consecutive CSR edges that share a row AND a 16-edge block (the stretch one
+// thread of an edge kernel owns).  run id of edge e = e/16 + #(rows <= row[e] whose first edge is not on a
+// 16-boundary) = e/16 + mis[row[e]+1] with mis the exclusive scan of the flags below.  The edge kernels write
+// one 128-wide partial per run (coalesced); k_run_sum128 adds the runs of each row in order (deterministic).
+__global__ void k_run_flags(const int* __restrict__ rowptr, int N, int* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) flags[i] = (rowptr[i + 1] > rowptr[i]) && (rowptr[i] & 15);
+    if (i == N) flags[N] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_run_sum128(const float* __restrict__ runs, const int* __restrict__ rowptr,
+                                                     const int* __restrict__ mis, int N, int E_cap,
+                                                     float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps_per_grid) {
+        int e0 = rowptr[i], e1 = rowptr[i + 1];
+        if (e1 > E_cap) e1 = E_cap;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e1 > e0) {
+            const int m = mis[i + 1];
+            const int r0 = (e0 >> 4) + m, r1 = ((e1 - 1) >> 4) + m;
+            for (int r = r0; r <= r1; ++r) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(runs + (int64_t)r * ENF_H) + lane);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        reinterpret_cast<float4*>(out + (int64_t)i * ENF_H)[lane] = acc;
+    }
+}
+
 }  // namespace
+
+int enf_scan_int(int* a, int64_t n, int* sums, cudaStream_t st);
+
+// mis: N+2 ints (exclusive scan of the misaligned-start flags, total at [N+1]); scratch: enf_scan_scratch_ints(N+1)
+int enf_run_index(const int* rowptr, int N, int* mis, int* scratch, cudaStream_t st) {
+    if (N == 0) return ENF_OK;
+    enf_count_launch(), k_run_flags<<<(N + 1 + 255) / 256, 256, 0, st>>>(rowptr, N, mis);
+    ENF_CHECK_LAUNCH();
+    return enf_scan_int(mis, N + 1, scratch, st);
+}
+
+int enf_run_sum128(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out, cudaStream_t st) {
+    if (N == 0) return ENF_OK;
+    const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
+    enf_count_launch(), k_run_sum128<<<blocks, 256, 0, st>>>(runs, rowptr, mis, N, E_cap, out);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
 
 int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
                        cudaStream_t st) {

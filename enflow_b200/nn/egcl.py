@@ -83,12 +83,17 @@ class EGCL(nn.Module):
         if mode == 0:
             _lib.check(L.enflow_edge_fwd(p(row), p(col), p(e_dev), E, p(pos), p(box), p(P), p(S), p(lp), p(packed), nf,
                                          p(wr), p(z2), p(z3), p(s), p(trans), st))
+            _lib.check(L.enflow_segment_sum128(p(z2), p(rowptr), None, N, E, 1, p(agg), st))
         else:
             wimg = torch.empty(L.enflow_tc_pack_bytes(), dtype=torch.uint8, device=dev)
+            mis = torch.empty(N + 2, dtype=torch.int32, device=dev)
+            scratch = torch.empty(L.enflow_run_scratch_ints(N), dtype=torch.int32, device=dev)
+            runs = new(L.enflow_run_rows(E, N), H)
             _lib.check(L.enflow_tc_pack_layer(p(lp), nf, p(wimg), st))
+            _lib.check(L.enflow_run_index(p(rowptr), N, p(mis), p(scratch), st))
             _lib.check(L.enflow_edge_fwd_tc(mode, p(row), p(col), p(e_dev), E, p(pos), p(box), p(P), p(S), p(lp),
-                                            p(wimg), nf, p(z2), p(z3), p(s), p(trans), st))
-        _lib.check(L.enflow_segment_sum128(p(z2), p(rowptr), None, N, E, 1, p(agg), st))
+                                            p(wimg), nf, p(rowptr), p(mis), p(runs), p(s), p(trans), st))
+            _lib.check(L.enflow_run_sum128(p(runs), p(rowptr), p(mis), N, E, p(agg), st))
         _lib.check(L.enflow_segment_sum3(p(trans), p(rowptr), None, N, E, 1, float(self.coords_weight), 0, p(F), st))
         _lib.check(L.enflow_node_post_fwd(p(hf), p(agg), N, nf, p(lp), p(packed), p(z4), p(G), st))
         self.last = {'agg': agg, 'trans': trans, 's': s, 'z2': z2}

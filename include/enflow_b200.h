@@ -94,12 +94,22 @@ int enflow_edge_fwd(const int32_t* row, const int32_t* col, const int32_t* E_dev
                     int nf, float* wr_scratch, float* z2, float* z3, float* s, float* trans, void* stream);
 /* tensor-core variant of enflow_edge_fwd (tcgen05.mma, TMEM accumulators). wimg: enflow_tc_pack_bytes() bytes
  * written by enflow_tc_pack_layer (swizzled bf16 hi/lo images of edge_nn.2 / coord_nn.0 weights), 16-byte aligned.
- * mode 1: bf16x3 operand split, fp32-accurate; mode 2: plain bf16 operands. */
+ * mode 1: bf16x3 operand split, fp32-accurate; mode 2: plain bf16 operands.
+ * Instead of storing edge_attr [E,128] it reduces it over each row inside the kernel into per-"run" partials
+ * (a run = the edges of one row inside one 16-edge block): runs [enflow_run_rows(E_cap,N)][128], indexed through
+ * mis [N+2] from enflow_run_index; enflow_run_sum128 adds the runs of each row in order -> unsorted_segment_sum
+ * (enflow/utils/helpers.py:54-60) of edge_attr, deterministic. */
 int64_t enflow_tc_pack_bytes(void);
 int enflow_tc_pack_layer(const float* layer_params, int nf, void* wimg, void* stream);
+int64_t enflow_run_rows(int E_cap, int N);
+int64_t enflow_run_scratch_ints(int N);
+int enflow_run_index(const int32_t* rowptr, int N, int32_t* mis, int32_t* scratch, void* stream);
+int enflow_run_sum128(const float* runs, const int32_t* rowptr, const int32_t* mis, int N, int E_cap, float* out,
+                      void* stream);
 int enflow_edge_fwd_tc(int mode, const int32_t* row, const int32_t* col, const int32_t* E_dev, int E_cap,
                        const float* pos, const float* box, const float* P, const float* S, const float* layer_params,
-                       const void* wimg, int nf, float* z2, float* z3, float* s, float* trans, void* stream);
+                       const void* wimg, int nf, const int32_t* rowptr, const int32_t* mis, float* runs, float* s,
+                       float* trans, void* stream);
 int enflow_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* layer_params,
                          const float* packed, float* z4, float* G, void* stream);
 
