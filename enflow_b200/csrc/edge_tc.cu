@@ -82,24 +82,6 @@ __device__ __forceinline__ void store_chunk(unsigned char* A, int row, int chunk
     }
 }
 
-// D^T[n][e] (+)= sum_k W[n][k] X[e][k].  A = weight image (K-major, rows = output unit n); B = activation
-// image, either K-major (rows = edge e, cols = k: the x1 image) or MN-major (rows = k, cols = e: the x2^T image
-// the transposed epilogue writes).  SPLIT adds the two cross terms of the bf16 hi/lo operand split.
-template <bool SPLIT, bool B_MN>
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t w_base, uint32_t x_base, uint32_t idesc) {
-    auto bdesc = [&](uint32_t base, int ks) { return B_MN ? tc::desc_mnmajor(base, ks) : tc::desc_kmajor(base, ks); };
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) tc::mma_f16(tmem_d, tc::desc_kmajor(w_base, ks), bdesc(x_base, ks), idesc, ks > 0);
-    if (SPLIT) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)      // hi(W) . lo(X)
-            tc::mma_f16(tmem_d, tc::desc_kmajor(w_base, ks), bdesc(x_base + tc::IMG_BYTES, ks), idesc, true);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)      // lo(W) . hi(X)
-            tc::mma_f16(tmem_d, tc::desc_kmajor(w_base + tc::IMG_BYTES, ks), bdesc(x_base, ks), idesc, true);
-    }
-}
-
 // 32x32 transpose-reduce across a warp: on return v[0] of lane l holds sum over lanes of (their) v[l]
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
@@ -167,6 +149,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     const uint32_t x_base = tc::smem_u32(A);
     const uint32_t w2_base = tc::smem_u32(Wimg);
     const uint32_t w3_base = tc::smem_u32(Wimg + (size_t)(SPLIT ? 2 : 1) * tc::IMG_BYTES);
+    const uint64_t dW2 = tc::make_desc(w2_base, 16, 1024), dW3 = tc::make_desc(w3_base, 16, 1024);
+    const uint64_t dXk = tc::make_desc(x_base, 16, 1024), dXmn = tc::make_desc(x_base, tc::BLK_BYTES, 1024);
     const uint32_t idesc_kk = tc::make_idesc(false, false);
     const uint32_t idesc_kmn = tc::make_idesc(false, true);
     const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)ec;
@@ -222,7 +206,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         __syncthreads();
         if (tid == 0) {             // z2^T = W2 x1^T on the tensor core
             tc::fence_after_sync();
-            issue_gemm<SPLIT, false>(tmem, w2_base, x_base, idesc_kk);
+            // z2^T[n][e] = sum_k W2[n][k] x1[e][k]: A = weight image, B = x1 image, both K-major
+            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffK128>(tmem, dW2, tc::IMG_BYTES, dXk, tc::IMG_BYTES, idesc_kk, false);
             tc::mma_commit(bar_mma);
         }
         tc::mbar_wait(bar_mma, parity);
@@ -270,7 +255,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         __syncthreads();
         if (tid == 0) {             // z3^T = W3 x2^T  (B read MN-major)
             tc::fence_after_sync();
-            issue_gemm<SPLIT, true>(tmem, w3_base, x_base, idesc_kmn);
+            // z3^T = W3 x2^T: B is the [hidden][edge] image the epilogue wrote, read MN-major
+            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem, dW3, tc::IMG_BYTES, dXmn, tc::IMG_BYTES, idesc_kmn, false);
             tc::mma_commit(bar_mma);
         }
         tc::mbar_wait(bar_mma, parity);

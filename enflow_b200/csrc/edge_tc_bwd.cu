@@ -68,18 +68,6 @@ __device__ __forceinline__ void store8(unsigned char* img, uint32_t off, const f
     }
 }
 
-// generic 3-term (or 1-term) GEMM issue. da(base, ks) / db(base, ks) build the descriptors of one image;
-// lo images sit a_lo / b_lo bytes after the hi images.
-template <bool SPLIT, typename FA, typename FB>
-__device__ __forceinline__ void issue(uint32_t tmem_d, int ksteps, uint32_t a, uint32_t a_lo, uint32_t b, uint32_t b_lo,
-                                      uint32_t idesc, bool acc_first, FA da, FB db) {
-    for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16(tmem_d, da(a, ks), db(b, ks), idesc, acc_first || ks > 0);
-    if (SPLIT) {
-        for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16(tmem_d, da(a, ks), db(b + b_lo, ks), idesc, true);
-        for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16(tmem_d, da(a + a_lo, ks), db(b, ks), idesc, true);
-    }
-}
-
 // sum over the 32 lanes of 16 per-lane values; lane l receives column (l & 15)
 __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
 #pragma unroll
@@ -155,14 +143,13 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     const uint32_t id_kk64 = tc::make_idesc(false, false, 64), id_kmn64 = tc::make_idesc(false, true, 64);
     const uint32_t id_mm64 = tc::make_idesc(true, true, 64);
     const uint32_t id_kk128 = tc::make_idesc(false, false, 128), id_kmn128 = tc::make_idesc(false, true, 128);
-    // descriptor builders for the image shapes in play
-    auto dW_k = [](uint32_t b, int ks) { return tc::desc_k(b, ks, tc::BLK_BYTES); };     // W [n][k] K-major
-    auto dW_mn = [](uint32_t b, int ks) { return tc::desc_mn(b, ks, tc::BLK_BYTES); };   // W read as [K=n][M=k]
-    auto dX1_k = [](uint32_t b, int ks) { return tc::desc_k(b, ks, X1_BLK); };           // x1 [e][k], K = k
-    auto dX1_mn = [](uint32_t b, int ks) { return tc::desc_mn(b, ks, X1_BLK); };         // x1 rows = K = e, N = k
-    auto dT_k = [](uint32_t b, int ks) { return tc::desc_k(b, ks, 0); };                 // [n][e], K = e (4 steps)
-    auto dT_mn = [](uint32_t b, int ks) { return tc::desc_mn(b, ks, tc::BLK_BYTES); };   // [n][e] rows = K = n, N = e
-
+    // base descriptors (K-major: LBO unused, SBO = 1024; MN-major: LBO = distance between 64-wide M/N blocks)
+    const uint64_t dW2k = tc::make_desc(w2, 16, 1024), dW3k = tc::make_desc(w3, 16, 1024);
+    const uint64_t dW2m = tc::make_desc(w2, tc::BLK_BYTES, 1024), dW3m = tc::make_desc(w3, tc::BLK_BYTES, 1024);
+    const uint64_t dXk = tc::make_desc(xb, 16, 1024);                  // x1 [e][k] K-major / x2^T [k][e] K-major
+    const uint64_t dX1m = tc::make_desc(xb, X1_BLK, 1024);             // x1 [e][k] read with rows = K = e
+    const uint64_t dXTm = tc::make_desc(xb, tc::BLK_BYTES, 1024);      // x2^T [k][e] read with rows = K = k
+    const uint64_t dZk = tc::make_desc(zb, 16, 1024), dZm = tc::make_desc(zb, tc::BLK_BYTES, 1024);
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
     uint32_t parity = 0;
     float gb2 = 0.f, gb3 = 0.f, gwc = 0.f, gwr = 0.f;
@@ -251,7 +238,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         __syncthreads();
         gen_x1();
         // ---- T1 = W2 x1^T
-        run_mma([&]() { issue<SPLIT>(tmem + T1_COL, 8, w2, WLO, xb, ALO, id_kk64, false, dW_k, dX1_k); });
+        run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffK64>(tmem + T1_COL, dW2k, WLO, dXk, ALO, id_kk64, false); });
         float z2r[16];
         {
             tc::tmem_ld16(lane_base + T1_COL + ec, z2r);
@@ -268,7 +255,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             }
         }
         // ---- T2 = W3 x2^T
-        run_mma([&]() { issue<SPLIT>(tmem + T2_COL, 8, w3, WLO, xb, ALO, id_kmn64, false, dW_k, dT_mn); });
+        run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T2_COL, dW3k, WLO, dXTm, ALO, id_kmn64, false); });
         {
             float v[16];
             tc::tmem_ld16(lane_base + T2_COL + ec, v);
@@ -291,8 +278,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         }
         // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T   (while the tensor pipe runs: gather dagg, form silu'(z2))
         issue_mma([&]() {
-            issue<SPLIT>(tmem + TW3_COL, 4, zb, ALO, xb, ALO, id_kk128, !first_tile, dT_k, dT_k);
-            issue<SPLIT>(tmem + T2_COL, 8, w3, WLO, zb, ALO, id_mm64, false, dW_mn, dT_mn);
+            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW3_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
+            tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T2_COL, dW3m, WLO, dZm, ALO, id_mm64, false);
         });
         float da[16];
 #pragma unroll
@@ -323,8 +310,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         gen_x1();                                                       // x2^T is dead: rebuild x1 in XB
         // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   (meanwhile: recompute z1 and silu'(z1) for this thread's edges)
         issue_mma([&]() {
-            issue<SPLIT>(tmem + TW2_COL, 4, zb, ALO, xb, ALO, id_kmn128, !first_tile, dT_k, dX1_mn);
-            issue<SPLIT>(tmem + T1_COL, 8, w2, WLO, zb, ALO, id_mm64, false, dW_mn, dT_mn);
+            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffMN>(tmem + TW2_COL, dZk, ALO, dX1m, ALO, id_kmn128, !first_tile);
+            tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T1_COL, dW2m, WLO, dZm, ALO, id_mm64, false);
         });
         first_tile = false;
         float ds1[16];

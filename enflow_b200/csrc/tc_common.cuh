@@ -85,6 +85,19 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- cheap MMA issue: base descriptors are built once, per-k-step offsets are compile-time constants ---------
+// (the start-address field counts 16-byte units and never carries out of its 14 bits for a 227 KB window)
+struct OffK128 { static constexpr uint32_t off(int ks) { return (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32); } };  // K-major, 128-row image
+struct OffK64  { static constexpr uint32_t off(int ks) { return (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32); } };        // K-major, 64-row image
+struct OffK    { static constexpr uint32_t off(int ks) { return (uint32_t)(ks * 32); } };                                   // K-major inside one 64-col block
+struct OffMN   { static constexpr uint32_t off(int ks) { return (uint32_t)(ks * 2048); } };                                 // MN-major: 16 rows per k-step
+__device__ __forceinline__ uint64_t desc_at(uint64_t d, uint32_t off_bytes) { return d + (uint64_t)(off_bytes >> 4); }
+
+// one GEMM = 1 (bf16) or 3 (bf16x3 split: hi.hi, hi.lo, lo.hi) chains of KS MMAs, fully unrolled
+template <bool SPLIT, int KS, typename OA, typename OB>
+__device__ __forceinline__ void issue_gemm_t(uint32_t tmem_d, uint64_t a, uint32_t a_lo_bytes, uint64_t b,
+                                             uint32_t b_lo_bytes, uint32_t idesc, bool acc_first);
+
 // ---- TMEM ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {      // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
@@ -173,6 +186,21 @@ __device__ __forceinline__ float sigmoid_sfu(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return r;
+}
+
+template <bool SPLIT, int KS, typename OA, typename OB>
+__device__ __forceinline__ void issue_gemm_t(uint32_t tmem_d, uint64_t a, uint32_t a_lo_bytes, uint64_t b,
+                                             uint32_t b_lo_bytes, uint32_t idesc, bool acc_first) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+        mma_f16(tmem_d, desc_at(a, OA::off(ks)), desc_at(b, OB::off(ks)), idesc, acc_first || ks > 0);
+    if (SPLIT) {
+        const uint64_t al = desc_at(a, a_lo_bytes), bl = desc_at(b, b_lo_bytes);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_f16(tmem_d, desc_at(a, OA::off(ks)), desc_at(bl, OB::off(ks)), idesc, true);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_f16(tmem_d, desc_at(al, OA::off(ks)), desc_at(b, OB::off(ks)), idesc, true);
+    }
 }
 
 }  // namespace tc
