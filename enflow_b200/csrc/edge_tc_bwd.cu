@@ -2,11 +2,11 @@
 // without reading any saved [E,H] activation (enflow/nn/egcl.py:57-63,71-75 differentiated by hand).
 //
 // All GEMMs keep the accumulator TRANSPOSED (TMEM lane = hidden unit, column = edge or weight column):
-//   T1 [n][e] = W2 x1^T            A = W2 image (K-major)          B = x1 image   [e][k] (K-major)
+//   T1 [n][e] = W2 x1^T            A = W2 image (K-major)          B = x1^T image [k][e] (MN-major)
 //   T2 [n][e] = W3 x2^T            A = W3 image (K-major)          B = x2^T image [k][e] (MN-major)
 //   TW3[n][k] += dz3^T x2          A = dz3^T image [n][e] (K-major) B = x2^T image [k][e] (K-major)
 //   T2 [k][e] = W3^T dz3^T         A = W3 image (MN-major)         B = dz3^T image [n][e] (MN-major)
-//   TW2[n][k] += dz2^T x1          A = dz2^T image [n][e] (K-major) B = x1 image   [e][k] (MN-major)
+//   TW2[n][k] += dz2^T x1          A = dz2^T image [n][e] (K-major) B = x1^T image [k][e] (K-major)
 //   T1 [k][e] = W2^T dz2^T         A = W2 image (MN-major)         B = dz2^T image [n][e] (MN-major)
 // One swizzled image per operand serves every view (tc_common.cuh).  The weight-gradient accumulators TW2/TW3
 // stay in TMEM for the whole life of the CTA and are written once at the end as a per-CTA partial; partials are
@@ -22,7 +22,6 @@ namespace {
 constexpr int THREADS = 512;
 constexpr int TE = 64;                     // edges per tile
 constexpr int ACT_IMG = 128 * TE * 2;      // one bf16 activation image: 16 KB
-constexpr int X1_BLK = TE * 128;           // block stride of the [e][k] image
 constexpr uint32_t T1_COL = 0, T2_COL = 64, TW2_COL = 128, TW3_COL = 256, TMEM_COLS = 512;
 
 struct TileInfoB {
@@ -43,9 +42,6 @@ struct SmemB {
     static constexpr size_t total = bar_off + 64 + 1024;
 };
 
-__device__ __forceinline__ uint32_t x1_off(int e, int chunk16) {          // [e][k] image, 64 rows
-    return (uint32_t)((chunk16 >> 3) * X1_BLK + e * 128 + (((chunk16 & 7) ^ (e & 7)) << 4));
-}
 __device__ __forceinline__ uint32_t t_off_(int n, int chunk8) {           // [n][e] image, 128 rows x 64 cols
     return (uint32_t)(n * 128 + ((chunk8 ^ (n & 7)) << 4));
 }
@@ -122,8 +118,6 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     __syncwarp();
     if (w == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     const float b2n = b2[n], b3n = b3[n], wcn = wc[n], wrn = W1[n * e1 + e1 - 1];
-    const float4 wr4 = make_float4(W1[(4 * lane + 0) * e1 + e1 - 1], W1[(4 * lane + 1) * e1 + e1 - 1],
-                                   W1[(4 * lane + 2) * e1 + e1 - 1], W1[(4 * lane + 3) * e1 + e1 - 1]);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -140,15 +134,14 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     const uint32_t xb = tc::smem_u32(XB), zb = tc::smem_u32(ZB);
     const uint32_t w2 = tc::smem_u32(Wimg), w3 = tc::smem_u32(Wimg + (size_t)(SPLIT ? 2 : 1) * tc::IMG_BYTES);
     const uint32_t WLO = tc::IMG_BYTES, ALO = ACT_IMG;
-    const uint32_t id_kk64 = tc::make_idesc(false, false, 64), id_kmn64 = tc::make_idesc(false, true, 64);
+    const uint32_t id_kmn64 = tc::make_idesc(false, true, 64);
     const uint32_t id_mm64 = tc::make_idesc(true, true, 64);
-    const uint32_t id_kk128 = tc::make_idesc(false, false, 128), id_kmn128 = tc::make_idesc(false, true, 128);
+    const uint32_t id_kk128 = tc::make_idesc(false, false, 128);
     // base descriptors (K-major: LBO unused, SBO = 1024; MN-major: LBO = distance between 64-wide M/N blocks)
     const uint64_t dW2k = tc::make_desc(w2, 16, 1024), dW3k = tc::make_desc(w3, 16, 1024);
     const uint64_t dW2m = tc::make_desc(w2, tc::BLK_BYTES, 1024), dW3m = tc::make_desc(w3, tc::BLK_BYTES, 1024);
-    const uint64_t dXk = tc::make_desc(xb, 16, 1024);                  // x1 [e][k] K-major / x2^T [k][e] K-major
-    const uint64_t dX1m = tc::make_desc(xb, X1_BLK, 1024);             // x1 [e][k] read with rows = K = e
-    const uint64_t dXTm = tc::make_desc(xb, tc::BLK_BYTES, 1024);      // x2^T [k][e] read with rows = K = k
+    const uint64_t dXk = tc::make_desc(xb, 16, 1024);                  // x1^T / x2^T [k][e] read K-major (K = e)
+    const uint64_t dXTm = tc::make_desc(xb, tc::BLK_BYTES, 1024);      // x1^T / x2^T [k][e] read with rows = K = k
     const uint64_t dZk = tc::make_desc(zb, 16, 1024), dZm = tc::make_desc(zb, tc::BLK_BYTES, 1024);
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
     uint32_t parity = 0;
@@ -158,29 +151,24 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     const int E = E_dev[0];
     const int tiles = (E + TE - 1) / TE;
 
-    // x1 = silu(P[row] + S[col] + w_r r) into XB as the [e][k] image: one warp per edge row
-    auto gen_x1 = [&]() {
+    // x1^T = silu(P[row] + S[col] + w_r r)^T into XB as the [hidden][edge] image, by the same (hidden unit,
+    // 16 edges) threads that run the epilogues (row reads coalesce over the 32 hidden units of a warp);
+    // ds1 != nullptr also returns silu'(z1) for the last epilogue
+    auto gen_x1 = [&](float* ds1) {
 #pragma unroll
-        for (int it = 0; it < TE / 16; ++it) {
-            const int m = w + 16 * it;
-            const float r = ti.r[m];
-            const float4 p = __ldg(reinterpret_cast<const float4*>(P + (int64_t)ti.row[m] * ENF_H) + lane);
-            const float4 s = __ldg(reinterpret_cast<const float4*>(S + (int64_t)ti.col[m] * ENF_H) + lane);
-            float x[4] = {fmaf(wr4.x, r, p.x + s.x), fmaf(wr4.y, r, p.y + s.y), fmaf(wr4.z, r, p.z + s.z),
-                          fmaf(wr4.w, r, p.w + s.w)};
-            const bool ok = ti.valid[m];
+        for (int ch = 0; ch < 2; ++ch) {
+            float x[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = ok ? x[j] * tc::sigmoid_sfu(x[j]) : 0.f;
-            const uint32_t off = x1_off(m, lane >> 1) + ((lane & 1) << 3);
-            if (SPLIT) {
-                uint2 hi, lo;
-                tc::split2(x[0], x[1], hi.x, lo.x);
-                tc::split2(x[2], x[3], hi.y, lo.y);
-                *reinterpret_cast<uint2*>(XB + off) = hi;
-                *reinterpret_cast<uint2*>(XB + ACT_IMG + off) = lo;
-            } else {
-                *reinterpret_cast<uint2*>(XB + off) = make_uint2(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]));
+            for (int j = 0; j < 8; ++j) {
+                const int m = ec + 8 * ch + j;
+                const bool ok = ti.valid[m];
+                const float z = ok ? fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) +
+                                                          __ldg(S + (int64_t)ti.col[m] * ENF_H + n)) : 0.f;
+                const float sg = tc::sigmoid_sfu(z);
+                x[j] = ok ? z * sg : 0.f;
+                if (ds1) ds1[8 * ch + j] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;
             }
+            store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);
         }
     };
     auto issue_mma = [&](auto&& body) {          // one thread issues
@@ -236,22 +224,25 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             ti.ddir[tid][0] = q0; ti.ddir[tid][1] = q1; ti.ddir[tid][2] = q2;
         }
         __syncthreads();
-        gen_x1();
+        gen_x1(nullptr);
         // ---- T1 = W2 x1^T
-        run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffK64>(tmem + T1_COL, dW2k, WLO, dXk, ALO, id_kk64, false); });
-        float z2r[16];
+        run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T1_COL, dW2k, WLO, dXTm, ALO, id_kmn64, false); });
+        float dsl2[16];                 // silu'(z2), consumed two phases later
         {
-            tc::tmem_ld16(lane_base + T1_COL + ec, z2r);
+            tc::tmem_ld16(lane_base + T1_COL + ec, dsl2);
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 float x[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int jj = 8 * ch + j;
-                    z2r[jj] += b2n;
-                    x[j] = ti.valid[ec + jj] ? z2r[jj] * tc::sigmoid_sfu(z2r[jj]) : 0.f;
+                    const bool ok = ti.valid[ec + jj];
+                    const float z = dsl2[jj] + b2n;
+                    const float sg = tc::sigmoid_sfu(z);
+                    x[j] = ok ? z * sg : 0.f;
+                    dsl2[jj] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;
                 }
-                store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);          // x2^T image [k][e]
+                store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);          // x2^T image [k][e] over x1^T
             }
         }
         // ---- T2 = W3 x2^T
@@ -276,20 +267,15 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                 store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz3^T image [n][e]
             }
         }
-        // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T   (while the tensor pipe runs: gather dagg, form silu'(z2))
+        // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T   (while the tensor pipe runs: gather dagg)
         issue_mma([&]() {
             tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW3_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T2_COL, dW3m, WLO, dZm, ALO, id_mm64, false);
         });
         float da[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const bool ok = ti.valid[ec + j];
-            da[j] = ok ? __ldg(dagg + (int64_t)ti.row[ec + j] * ENF_H + n) : 0.f;
-            const float z = z2r[j];
-            const float sg = tc::sigmoid_sfu(z);
-            z2r[j] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;            // now holds silu'(z2)
-        }
+        for (int j = 0; j < 16; ++j)
+            da[j] = ti.valid[ec + j] ? __ldg(dagg + (int64_t)ti.row[ec + j] * ENF_H + n) : 0.f;
         wait_mma();
         {
             float v[16];
@@ -300,29 +286,21 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int jj = 8 * ch + j;
-                    const float dz = (v[jj] + da[jj]) * z2r[jj];
+                    const float dz = (v[jj] + da[jj]) * dsl2[jj];
                     gb2 += dz;
                     x[j] = dz;
                 }
                 store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz2^T image [n][e]
             }
         }
-        gen_x1();                                                       // x2^T is dead: rebuild x1 in XB
-        // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   (meanwhile: recompute z1 and silu'(z1) for this thread's edges)
+        float ds1[16];
+        gen_x1(ds1);                                                    // x2^T is dead: rebuild x1^T, keep silu'(z1)
+        // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   
         issue_mma([&]() {
-            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffMN>(tmem + TW2_COL, dZk, ALO, dX1m, ALO, id_kmn128, !first_tile);
+            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW2_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T1_COL, dW2m, WLO, dZm, ALO, id_mm64, false);
         });
         first_tile = false;
-        float ds1[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int m = ec + j;
-            const bool ok = ti.valid[m];
-            const float z = ok ? fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) + __ldg(S + (int64_t)ti.col[m] * ENF_H + n)) : 0.f;
-            const float sg = tc::sigmoid_sfu(z);
-            ds1[j] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;
-        }
         wait_mma();
         {
             float v[16];
