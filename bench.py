@@ -285,7 +285,7 @@ def main():
             kname = 'k_' + dom + ('_tc' if tc_mode else '')
             # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
             # (profiles/r1_edge_bwd_tc_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
-            traffic = {'k_edge_bwd_tc': 459.4e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
+            traffic = {'k_edge_bwd_tc': 496.9e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
             mma_per_gemm = {'fp32': 0, 'fp32_tc': 3, 'bf16': 1}[args.precision]
             roof = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'],
                     'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
@@ -317,8 +317,8 @@ def main():
                        'step': ('LFIntegrator.reverse (inverse pass, no collective)' if generate else
                                 'forward + Alchemical_NLL + backward (all parameter grads)'
                                 + (' + NCCL all-reduce of the flat gradient buffer' if world > 1 else '') + ' + Adam'),
-                       'parallelism': f'dp{world}', 'l2': 'no explicit flush: every step streams the saved edge '
-                       'activations (2*L*E*H*4 bytes, far above the 126 MB L2) through HBM'},
+                       'parallelism': f'dp{world}', 'l2': 'no explicit flush: every layer of every step streams E*H*4 bytes of '
+                       'edge gradients (dz1, 426 MB at this shape) plus the run partials through HBM, far above the 126 MB L2'},
             'clocks': clocks,
             'e2e': {'value': mols * args.steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'last_loss': loss_host},
