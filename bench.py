@@ -148,6 +148,7 @@ def main():
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='fp32_tc', choices=['fp32', 'fp32_tc', 'bf16'])
+    ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
@@ -181,7 +182,7 @@ def main():
         dist.broadcast(model.flat_params, 0)
         model._dp_group = dist.group.WORLD
     nll = Alchemical_NLL(kBT=syn.TRAIN_KBT, softening=syn.TRAIN_SOFTENING)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
 
     # per-rank synthetic batch (weak scaling: fixed per-GPU batch), pinned host copy + resident device copy
     arrs = syn.make_batch(config, batch, seed=1234 + 10 * rank + {'c1': 1, 'c2': 2, 'c3': 3, 'c4': 4, 'c5': 5}[config], **kwargs)
@@ -225,44 +226,68 @@ def main():
     if E is None:
         E = int(model._edge_caps[(batch, n_atoms)] / 1.25)
 
-    # end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
-    barrier()
-    model.check_status = True          # capacity overflow would be caught (and the step redone) here too
+    # The whole step (forward C call, likelihood, backward C call, all-reduce, Adam) has no host synchronisation, so it
+    # is captured once in a CUDA graph and replayed (enflow_b200.graph); --no-graph launches every kernel eagerly.
+    L = _lib.lib()
+    gstep, graph_note, launches_per_step = None, 'eager launches', None
+    if not generate and not args.no_graph:
+        try:
+            from enflow_b200.graph import GraphedTrainStep
+            L.enflow_launch_count(1)
+            gstep = GraphedTrainStep(model, nll, opt, resident, warmup=1)
+            launches_per_step = int(L.enflow_launch_count(1)) // 2      # 1 eager warm-up + 1 captured step
+            graph_note = 'CUDA graph replay of the whole step'
+        except Exception as exc:      # keep measuring: eager path
+            gstep, graph_note = None, f'eager launches (graph capture failed: {type(exc).__name__})'
+            torch.cuda.synchronize()
+
+    def run_resident():
+        return gstep() if gstep is not None else step(view(resident))
+
+    def run_host():          # H2D of the batch from pinned host memory every step
+        return gstep(host) if gstep is not None else step(host.to(dev))
+
+    # ---- end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
+    model.check_status = gstep is None
     for _ in range(args.warmup):       # warm the host-buffer path too (allocator growth for the per-step device batch)
-        step(host.to(dev)).item()
-    torch.cuda.synchronize()
+        run_host().item()
+    barrier()
     t0 = time.perf_counter()
-    e2e_steps = []
     for _ in range(args.steps):
-        ts = time.perf_counter()
-        d = host.to(dev)
-        loss = step(d)
-        loss_host = loss.item()
-        e2e_steps.append(time.perf_counter() - ts)
+        loss_host = run_host().item()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if os.environ.get('ENFLOW_BENCH_DEBUG'):
-        print('e2e per-step ms:', [round(1e3 * x, 2) for x in e2e_steps], file=sys.stderr)
     model.check_status = False
+
+    # ---- device-timed region: inputs resident in HBM, K steps between CUDA events
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.5)        # let nvidia-smi spin up so samples fall inside the (short) timed region
-    L = _lib.lib()
-    L.enflow_launch_count(1)
-    L.enflow_timing_enable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.enflow_launch_count(1)
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        step(view(resident))
+        run_resident()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    launches = launches_per_step * args.steps if gstep is not None else int(L.enflow_launch_count(1))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel durations: the same steps launched eagerly with CUDA events around every kernel family
+    L.enflow_timing_enable(1)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev2.record()
+    for _ in range(args.steps):
+        step(view(resident))
+    ev3.record()
+    barrier()
+    ms_eager = ev2.elapsed_time(ev3)
     fam = _lib.timing_read()
     L.enflow_timing_enable(0)
-    launches = int(L.enflow_launch_count(1))
-    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,7 +300,7 @@ def main():
         mols = batch * world
         # dominant kernel + the HBM-bound kernels the north star names
         avg = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in fam.items()}
-        share = {k: v[0] / ms_total for k, v in fam.items()}
+        share = {k: v[0] / ms_eager for k, v in fam.items()}
         dom = max(fam, key=lambda k: fam[k][0])
         flops = {'edge_fwd': edge_flops(E, nf, False), 'edge_bwd': 2 * edge_flops(E, nf, False)}
         roof = None
@@ -323,6 +348,8 @@ def main():
             'e2e': {'value': mols * args.steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'last_loss': loss_host},
             'gpu_launches': launches,
+            'launch_mode': graph_note,
+            'eager_ms_per_step': ms_eager / args.steps,
             'roofline': roof,
             'roofline_hbm_kernels': hbm,
             'kernel_ms_per_step': {k: v[0] / args.steps for k, v in fam.items()},
