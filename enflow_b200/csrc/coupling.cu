@@ -7,38 +7,44 @@
 
 namespace {
 
-// one warp per molecule, lanes stride over its atoms
+// One CTA per group of mols_per_cta consecutive molecules.  Their atoms are contiguous, so the [*,3] and [*,nf]
+// arrays are walked as flat element ranges (every load/store fully coalesced, all 32 lanes busy whatever the
+// molecule size); the per-molecule sum of Q is then a warp reduction (one warp per molecule, fixed xor tree).
+
 __global__ void __launch_bounds__(256) k_coupling_fwd(const float* __restrict__ Q, const float* __restrict__ F,
                                                        const float* __restrict__ G, const float* __restrict__ h,
                                                        const float* __restrict__ g, const float* __restrict__ pos,
                                                        const float* __restrict__ vel, const float* __restrict__ box,
                                                        const int* __restrict__ mol_off, int B, int nf, float dt,
-                                                       float* __restrict__ h_o, float* __restrict__ g_o,
-                                                       float* __restrict__ pos_o, float* __restrict__ vel_o,
-                                                       float* __restrict__ ldj_mol) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < B; m += warps) {
-        const int a0 = mol_off[m], a1 = mol_off[m + 1];
-        float qs = 0.f;
-        for (int i = a0 + lane; i < a1; i += 32) {
-            const float q = Q[i];
-            const float s = expf(q);
-            qs += q;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = fmaf(s, vel[(int64_t)i * 3 + c], F[(int64_t)i * 3 + c] * dt);
-                vel_o[(int64_t)i * 3 + c] = v;
-                pos_o[(int64_t)i * 3 + c] = wrapf_(fmaf(v, dt, pos[(int64_t)i * 3 + c]), box[(int64_t)i * 3 + c]);
-            }
-            for (int c = 0; c < nf; ++c) {
-                const float gn = fmaf(G[(int64_t)i * nf + c], dt, g[(int64_t)i * nf + c]);
-                g_o[(int64_t)i * nf + c] = gn;
-                h_o[(int64_t)i * nf + c] = fmaf(gn, dt, h[(int64_t)i * nf + c]);
-            }
+                                                       int mols_per_cta, float* __restrict__ h_o,
+                                                       float* __restrict__ g_o, float* __restrict__ pos_o,
+                                                       float* __restrict__ vel_o, float* __restrict__ ldj_mol) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int m0 = blockIdx.x * mols_per_cta; m0 < B; m0 += gridDim.x * mols_per_cta) {
+        const int m1 = min(m0 + mols_per_cta, B);
+        const int a0 = mol_off[m0], a1 = mol_off[m1];
+        const int64_t v0 = 3LL * a0;
+        const int nv = 3 * (a1 - a0);
+        for (int t = threadIdx.x; t < nv; t += 256) {                         // vel, pos (dynamics.py:14,17-18)
+            const int64_t idx = v0 + t;
+            const float v = fmaf(expf(Q[a0 + t / 3]), vel[idx], F[idx] * dt);
+            vel_o[idx] = v;
+            pos_o[idx] = wrapf_(fmaf(v, dt, pos[idx]), box[idx]);
         }
-        qs = warp_sum(qs);
-        if (lane == 0) ldj_mol[m] += qs;
+        const int64_t f0 = (int64_t)nf * a0;
+        const int nfe = nf * (a1 - a0);
+        for (int t = threadIdx.x; t < nfe; t += 256) {                        // g, h (dynamics.py:15,19)
+            const int64_t idx = f0 + t;
+            const float gn = fmaf(G[idx], dt, g[idx]);
+            g_o[idx] = gn;
+            h_o[idx] = fmaf(gn, dt, h[idx]);
+        }
+        for (int m = m0 + wid; m < m1; m += 8) {                              // ldj += sum Q (dynamics.py:21, Q2)
+            float qs = 0.f;
+            for (int i = mol_off[m] + lane; i < mol_off[m + 1]; i += 32) qs += Q[i];
+            qs = warp_sum(qs);
+            if (lane == 0) ldj_mol[m] += qs;
+        }
     }
 }
 
@@ -125,8 +131,12 @@ int enf_coupling_fwd(const float* Q, const float* F, const float* G, const float
                      const float* pos, const float* vel, const float* box, const int* mol_off, int B, int nf,
                      float dt, float* h_o, float* g_o, float* pos_o, float* vel_o, float* ldj_mol, cudaStream_t st) {
     if (B == 0) return ENF_OK;
-    enf_count_launch(), k_coupling_fwd<<<mol_grid(B), 256, 0, st>>>(Q, F, G, h, g, pos, vel, box, mol_off, B, nf, dt, h_o, g_o, pos_o,
-                                                 vel_o, ldj_mol);
+    // enough CTAs to fill the machine twice at small batches, up to 32 molecules per CTA at large ones
+    int mpc = B / (2 * enf_num_sms());
+    mpc = mpc < 1 ? 1 : (mpc > 32 ? 32 : mpc);
+    const int cgrid = (B + mpc - 1) / mpc;
+    enf_count_launch(), k_coupling_fwd<<<cgrid, 256, 0, st>>>(Q, F, G, h, g, pos, vel, box, mol_off, B, nf, dt, mpc, h_o, g_o,
+                                                              pos_o, vel_o, ldj_mol);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
