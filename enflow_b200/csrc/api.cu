@@ -115,7 +115,7 @@ int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const f
 
 int enflow_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
                           const int* E_dev, int* colptr, int* perm, int* ws, void* stream) {
-    return enf_build_col_perm(col, rowptr, mol_off, B, N, E_cap, E_dev, colptr, perm, ws, ST(stream));
+    return enf_build_col_perm(col, rowptr, mol_off, B, N, E_cap, E_dev, colptr, perm, ws, nullptr, ST(stream));
 }
 
 int enflow_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu,

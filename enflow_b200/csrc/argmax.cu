@@ -179,8 +179,16 @@ __global__ void k_argmax_reduce(const float* __restrict__ partial, int n_cta, in
                                 int o_w0, int o_b0, int o_w2, int o_b2, float* __restrict__ grad) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= stride) return;
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c) acc += partial[(int64_t)c * stride + idx];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+        a0 += partial[(int64_t)(c + 0) * stride + idx];
+        a1 += partial[(int64_t)(c + 1) * stride + idx];
+        a2 += partial[(int64_t)(c + 2) * stride + idx];
+        a3 += partial[(int64_t)(c + 3) * stride + idx];
+    }
+    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * stride + idx];
+    const float acc = (a0 + a1) + (a2 + a3);
     int dst;
     const int s0 = ENF_H * nf, s1 = s0 + ENF_H, s2 = s1 + 2 * nf * ENF_H;
     if (idx < s0) dst = o_w0 + idx;

@@ -462,8 +462,16 @@ __global__ void k_edge_reduce(const float* __restrict__ partial, int n_cta, int 
                               int o_wc, int o_w1, int e1, float* __restrict__ grad) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= EDGE_PARTIAL) return;
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c) acc += partial[(int64_t)c * EDGE_PARTIAL + idx];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // fixed order: four interleaved chains
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+        a0 += partial[(int64_t)(c + 0) * EDGE_PARTIAL + idx];
+        a1 += partial[(int64_t)(c + 1) * EDGE_PARTIAL + idx];
+        a2 += partial[(int64_t)(c + 2) * EDGE_PARTIAL + idx];
+        a3 += partial[(int64_t)(c + 3) * EDGE_PARTIAL + idx];
+    }
+    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * EDGE_PARTIAL + idx];
+    const float acc = (a0 + a1) + (a2 + a3);
     const int HH = ENF_H * ENF_H;
     int dst;
     if (idx < HH) dst = o_w2 + idx;

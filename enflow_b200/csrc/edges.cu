@@ -200,7 +200,9 @@ __device__ __forceinline__ int block_exclusive(int v, int* total) {
     return pre + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const int* a0, const int* a1, int64_t n, int* sums, int nb) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const int* a0, const int* a1, int64_t n, int* sums, int nb,
+                                                            const int* skip) {
+    if (skip && *skip) return;
     const int* a = blockIdx.y ? a1 : a0;
     const int64_t b0 = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
     int s = 0;
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const int* a0, const
     if (threadIdx.x == 0) sums[blockIdx.y * nb + blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(int* sums, int nb) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(int* sums, int nb, const int* skip) {
+    if (skip && *skip) return;
     int* s = sums + blockIdx.y * nb;
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -230,7 +233,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(int* sums, int nb) {
 }
 
 // in place; element n (one past the end) receives the grand total
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int* a0, int* a1, int64_t n, const int* sums, int nb) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int* a0, int* a1, int64_t n, const int* sums, int nb,
+                                                             const int* skip) {
+    if (skip && *skip) return;
     int* a = blockIdx.y ? a1 : a0;
     const int64_t b0 = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
@@ -257,7 +262,9 @@ __global__ void k_edges_finish(const int* __restrict__ cnt_csr, int N, int E_cap
 }
 
 // ---- column-grouped permutation (CSR -> CSC), deterministic and stable in edge order ----
-__global__ void k_col_count(const int* __restrict__ col, const int* __restrict__ E_dev, int* __restrict__ colcnt) {
+__global__ void k_col_count(const int* __restrict__ col, const int* __restrict__ E_dev, int* __restrict__ colcnt,
+                            const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const int E = E_dev[0];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
         atomicAdd(&colcnt[col[e]], 1);       // integer adds: the result does not depend on order
@@ -266,7 +273,9 @@ __global__ void k_col_count(const int* __restrict__ col, const int* __restrict__
 // one CTA per molecule; chunks of 256 edges; rank among equal columns by comparison in smem
 __global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, const int* __restrict__ rowptr,
                                                    const int* __restrict__ mol_off, const int* __restrict__ colptr,
-                                                   int* __restrict__ cursor, int* __restrict__ perm, int E_cap) {
+                                                   int* __restrict__ cursor, int* __restrict__ perm, int E_cap,
+                                                   const int* __restrict__ skip) {
+    if (skip && *skip) return;
     __shared__ int ccol[256];
     const int m = blockIdx.x;
     const int e_begin = rowptr[mol_off[m]];
@@ -292,15 +301,35 @@ __global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, c
     }
 }
 
+__global__ void k_zero_int(int* __restrict__ p, int64_t n, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
+}
+
+// same[0] = 1 iff the two CSR edge lists are identical (used to reuse the column permutation between layers:
+// in the fully connected regime the neighbour list does not change from one coupling step to the next)
+__global__ void k_edges_same_init(const int* __restrict__ Ea, const int* __restrict__ Eb, int* __restrict__ same) {
+    same[0] = (Ea[0] == Eb[0] && Ea[1] == Eb[1]) ? 1 : 0;
+}
+__global__ void k_edges_same(const int* __restrict__ ra, const int* __restrict__ ca, const int* __restrict__ rb,
+                             const int* __restrict__ cb, const int* __restrict__ Ea, int* __restrict__ same) {
+    if (!same[0]) return;
+    const int E = Ea[0];
+    bool diff = false;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
+        diff |= (ra[e] != rb[e]) | (ca[e] != cb[e]);
+    if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicAnd(same, 0);
+}
+
 }  // namespace
 
-static int scan2(int* a0, int* a1, int64_t n, int* sums, cudaStream_t st) {
+static int scan2(int* a0, int* a1, int64_t n, int* sums, cudaStream_t st, const int* skip = nullptr) {
     const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     const int ny = a1 ? 2 : 1;
     dim3 g(nb, ny);
-    enf_count_launch(), k_scan_sums<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
-    enf_count_launch(), k_scan_top<<<dim3(1, ny), SCAN_THREADS, 0, st>>>(sums, nb);
-    enf_count_launch(), k_scan_apply<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb);
+    enf_count_launch(), k_scan_sums<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb, skip);
+    enf_count_launch(), k_scan_top<<<dim3(1, ny), SCAN_THREADS, 0, st>>>(sums, nb, skip);
+    enf_count_launch(), k_scan_apply<<<g, SCAN_THREADS, 0, st>>>(a0, a1, n, sums, nb, skip);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
@@ -350,21 +379,30 @@ template int enf_build_edges_t<float>(const float*, const float*, const float*, 
 template int enf_build_edges_t<double>(const double*, const double*, const float*, const int*, int, int, int, int*,
                                        int*, int*, int*, int*, int*, int*, cudaStream_t);
 
-// colptr [N+1], perm [E_cap]; ws is the same workspace handed to enf_build_edges_t (its atom_mol is reused)
+// colptr [N+1], perm [E_cap]; ws is the same workspace handed to enf_build_edges_t.
+// skip (nullable, device int): when non-zero every kernel returns at once and colptr/perm keep their contents.
 int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
-                       const int* E_dev, int* colptr, int* perm, int* ws, cudaStream_t st) {
+                       const int* E_dev, int* colptr, int* perm, int* ws, const int* skip, cudaStream_t st) {
     const int64_t n27 = 27LL * N;
     int* after_atom_mol = ws + 4 * n27 + 2 + 2LL * N;
     int* cursor = after_atom_mol;            // N
-    int* dummy = cursor + N;                 // second array for scan2 (N+1)
-    int* sums = dummy + N + 1;
-    cudaMemsetAsync(colptr, 0, sizeof(int) * (N + 1), st);
-    cudaMemsetAsync(cursor, 0, sizeof(int) * (2LL * N + 1), st);
-    enf_count_launch(), k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr);
+    int* sums = cursor + N + (N + 1);
+    const int zb = enf_num_sms() * 2;
+    enf_count_launch(), k_zero_int<<<zb, 256, 0, st>>>(colptr, N + 1, skip);
+    enf_count_launch(), k_zero_int<<<zb, 256, 0, st>>>(cursor, N, skip);
+    enf_count_launch(), k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr, skip);
     ENF_CHECK_LAUNCH();
-    ENF_TRY(scan2(colptr, dummy, N, sums, st));
-    cudaMemsetAsync(cursor, 0, sizeof(int) * N, st);
-    enf_count_launch(), k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap);
+    ENF_TRY(scan2(colptr, nullptr, N, sums, st, skip));
+    enf_count_launch(), k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap, skip);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
+// same[0] <- (edge list a == edge list b)
+int enf_edges_same(const int* row_a, const int* col_a, const int* E_a, const int* row_b, const int* col_b,
+                   const int* E_b, int* same, cudaStream_t st) {
+    enf_count_launch(), k_edges_same_init<<<1, 1, 0, st>>>(E_a, E_b, same);
+    enf_count_launch(), k_edges_same<<<enf_num_sms() * 4, 256, 0, st>>>(row_a, col_a, row_b, col_b, E_a, same);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

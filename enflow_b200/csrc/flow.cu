@@ -51,7 +51,7 @@ struct Workspace {
     float* log_q;
     // backward scratch
     float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd, *partial, *Qscratch;
-    int *colptr, *perm;
+    int *colptr, *perm, *same;
     size_t bytes;
 };
 
@@ -100,7 +100,7 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
         w.dz1 = b.take<float>(E * H); w.dd = b.take<float>(E * 3);
         w.partial = b.take<float>(partial_floats(d));
         w.Qscratch = b.take<float>(N);
-        w.colptr = b.take<int>(N + 1); w.perm = b.take<int>(E);
+        w.colptr = b.take<int>(N + 1); w.perm = b.take<int>(E); w.same = b.take<int>(4);
     }
     w.bytes = (b.off + 255) / 256 * 256;
     return w;
@@ -226,8 +226,16 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
                                              w.packed + (int64_t)l * enf_pack_offsets(nf).size, w.dagg, dh, lg, w.partial, st));
         // edge_model + force_model (egcl.py:57-63,71-75); P/S are recomputed, not stored
         TIMED(TK_NODE_PRE, enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
+        // column-grouped view of the edges; reused as is when this layer's list equals the one just processed
+        // (fully connected regime: the neighbour list is the same at every coupling step)
+        const int* skip = nullptr;
+        if (l < d.L - 1) {
+            const LayerSave& nx = w.layer[l + 1];
+            ENF_TRY(enf_edges_same(sv.row, sv.col, sv.E_dev, nx.row, nx.col, nx.E_dev, w.same, st));
+            skip = w.same;
+        }
         TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
-                                   w.edges_ws, st));
+                                              w.edges_ws, skip, st));
         if (d.mode == 0) {
             TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf,
                                             w.wr, sv.z2, sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg,

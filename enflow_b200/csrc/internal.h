@@ -8,7 +8,9 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
                       int* row, int* col, int* rowptr, int* ref_pos, int* E_dev, int* status, int* ws,
                       cudaStream_t st);
 int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
-                       const int* E_dev, int* colptr, int* perm, int* ws, cudaStream_t st);
+                       const int* E_dev, int* colptr, int* perm, int* ws, const int* skip, cudaStream_t st);
+int enf_edges_same(const int* row_a, const int* col_a, const int* E_a, const int* row_b, const int* col_b,
+                   const int* E_b, int* same, cudaStream_t st);
 
 int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
                        cudaStream_t st);

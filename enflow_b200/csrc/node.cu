@@ -146,8 +146,16 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int n_cta, 
     for (int s = 0; s < segs.n; ++s)
         if (idx >= segs.src[s] && idx < segs.src[s] + segs.len[s]) { seg = s; local = idx - segs.src[s]; }
     if (seg < 0) return;
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c) acc += partial[(int64_t)c * stride + idx];   // fixed CTA order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // fixed order: four interleaved chains
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+        a0 += partial[(int64_t)(c + 0) * stride + idx];
+        a1 += partial[(int64_t)(c + 1) * stride + idx];
+        a2 += partial[(int64_t)(c + 2) * stride + idx];
+        a3 += partial[(int64_t)(c + 3) * stride + idx];
+    }
+    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * stride + idx];
+    const float acc = (a0 + a1) + (a2 + a3);
     grad[segs.dst[seg] + local] += acc;
 }
 

@@ -217,8 +217,16 @@ __global__ void k_node_post_reduce(const float* __restrict__ partial, int n_cta,
                                    int o_b4, int o_w5, int o_b5, float* __restrict__ grad) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= stride) return;
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c) acc += partial[(int64_t)c * stride + idx];      // fixed CTA order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // fixed order: four interleaved chains, combined at the end
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+        a0 += partial[(int64_t)(c + 0) * stride + idx];
+        a1 += partial[(int64_t)(c + 1) * stride + idx];
+        a2 += partial[(int64_t)(c + 2) * stride + idx];
+        a3 += partial[(int64_t)(c + 3) * stride + idx];
+    }
+    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * stride + idx];
+    const float acc = (a0 + a1) + (a2 + a3);
     const int s0 = ENF_H * D, s1 = s0 + ENF_H, s2 = s1 + nf * ENF_H;
     int dst;
     if (idx < s0) dst = o_w4 + idx;
