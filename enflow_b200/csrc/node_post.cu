@@ -11,12 +11,16 @@ namespace {
 constexpr int PT = 32;          // nodes per tile
 constexpr int TPB = 256;
 constexpr int DP = 136;         // padded input width (nf + 128 <= 136), float4-aligned rows
-constexpr int JS = 17;          // input columns per warp in the wgrad (8 warps x 17 = 136)
+constexpr int JS = 9;           // backward: input columns per warp in the wgrad (16 warps x 9 = 144)
+constexpr int BT = 512;         // backward: threads per CTA (16 warps hide the shared-memory latency of the wgrad loop)
+constexpr int BPT = 64;         // backward: nodes per tile
+constexpr int BDP = 144;        // backward: padded input width
 
+template <int NODES, int STRIDE, int NTHREADS>
 __device__ __forceinline__ void load_inputs(float* in_s, const float* __restrict__ h, const float* __restrict__ agg,
                                             int t0, int N, int nf) {
-    for (int idx = threadIdx.x; idx < PT * DP; idx += TPB) {
-        const int t = idx / DP, j = idx - t * DP;
+    for (int idx = threadIdx.x; idx < NODES * STRIDE; idx += NTHREADS) {
+        const int t = idx / STRIDE, j = idx - t * STRIDE;
         float v = 0.f;
         if (t0 + t < N) {
             if (j < nf) v = h[(int64_t)(t0 + t) * nf + j];
@@ -26,62 +30,74 @@ __device__ __forceinline__ void load_inputs(float* in_s, const float* __restrict
     }
 }
 
-__global__ void __launch_bounds__(TPB) k_node_post_fwd(const float* __restrict__ h, const float* __restrict__ agg,
-                                                        int N, int nf, const float* __restrict__ W4T,
-                                                        const float* __restrict__ b4, const float* __restrict__ W5,
-                                                        const float* __restrict__ b5, float* __restrict__ z4,
-                                                        float* __restrict__ G) {
-    __shared__ __align__(16) float in_s[PT * DP];
+__global__ void __launch_bounds__(TPB, 2) k_node_post_fwd(const float* __restrict__ h, const float* __restrict__ agg,
+                                                           int N, int nf, const float* __restrict__ W4T,
+                                                           const float* __restrict__ b4, const float* __restrict__ W5,
+                                                           const float* __restrict__ b5, float* __restrict__ z4,
+                                                           float* __restrict__ G) {
+    extern __shared__ __align__(16) float smem_nf[];
+    float* w_s = smem_nf;                         // W4^T [D][H], staged once per (persistent) CTA
+    float* in_s = w_s + DP * ENF_H;               // [PT][DP]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int D = nf + ENF_H;
-    const int t0 = blockIdx.x * PT;
-    load_inputs(in_s, h, agg, t0, N, nf);
-    __syncthreads();
+    for (int idx = threadIdx.x; idx < D * ENF_H / 4; idx += TPB)
+        reinterpret_cast<float4*>(w_s)[idx] = __ldg(reinterpret_cast<const float4*>(W4T) + idx);
     const float4 bb = *reinterpret_cast<const float4*>(b4 + 4 * lane);
-    float acc[4][4];
+    const int tiles = (N + PT - 1) / PT;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int t0 = tile * PT;
+        __syncthreads();
+        load_inputs<PT, DP, TPB>(in_s, h, agg, t0, N, nf);
+        __syncthreads();
+        float acc[4][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { acc[t][0] = bb.x; acc[t][1] = bb.y; acc[t][2] = bb.z; acc[t][3] = bb.w; }
-    const float* in0 = in_s + (4 * w) * DP;
+        for (int t = 0; t < 4; ++t) { acc[t][0] = bb.x; acc[t][1] = bb.y; acc[t][2] = bb.z; acc[t][3] = bb.w; }
+        const float* in0 = in_s + (4 * w) * DP;
 #pragma unroll 4
-    for (int j = 0; j < D; ++j) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(W4T + (int64_t)j * ENF_H) + lane);
+        for (int j = 0; j < D; ++j) {
+            const float4 wv = *reinterpret_cast<const float4*>(w_s + j * ENF_H + 4 * lane);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float a = in0[t * DP + j];
-            acc[t][0] = fmaf(a, wv.x, acc[t][0]); acc[t][1] = fmaf(a, wv.y, acc[t][1]);
-            acc[t][2] = fmaf(a, wv.z, acc[t][2]); acc[t][3] = fmaf(a, wv.w, acc[t][3]);
+            for (int t = 0; t < 4; ++t) {
+                const float a = in0[t * DP + j];
+                acc[t][0] = fmaf(a, wv.x, acc[t][0]); acc[t][1] = fmaf(a, wv.y, acc[t][1]);
+                acc[t][2] = fmaf(a, wv.z, acc[t][2]); acc[t][3] = fmaf(a, wv.w, acc[t][3]);
+            }
         }
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int i = t0 + 4 * w + t;
-        if (i < N) *reinterpret_cast<float4*>(z4 + (int64_t)i * ENF_H + 4 * lane) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[t][c] = siluf_(acc[t][c]);
-    }
-    for (int c = 0; c < nf; ++c) {
-        const float4 w5 = __ldg(reinterpret_cast<const float4*>(W5 + c * ENF_H) + lane);
-        const float bc = b5[c];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            float p = fmaf(w5.x, acc[t][0], fmaf(w5.y, acc[t][1], fmaf(w5.z, acc[t][2], w5.w * acc[t][3])));
-            p = warp_sum(p);
             const int i = t0 + 4 * w + t;
-            if (lane == 0 && i < N) G[(int64_t)i * nf + c] = p + bc;
+            if (i < N) *reinterpret_cast<float4*>(z4 + (int64_t)i * ENF_H + 4 * lane) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[t][c] = siluf_(acc[t][c]);
+        }
+        for (int c = 0; c < nf; ++c) {
+            const float4 w5 = __ldg(reinterpret_cast<const float4*>(W5 + c * ENF_H) + lane);
+            const float bc = b5[c];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float p = fmaf(w5.x, acc[t][0], fmaf(w5.y, acc[t][1], fmaf(w5.z, acc[t][2], w5.w * acc[t][3])));
+                p = warp_sum(p);
+                const int i = t0 + 4 * w + t;
+                if (lane == 0 && i < N) G[(int64_t)i * nf + c] = p + bc;
+            }
         }
     }
 }
 
 // per-CTA partial (floats): dW4 [H*D] (native [k][j]) | db4 [H] | dW5 [nf*H] | db5 [nf]
-__global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restrict__ h, const float* __restrict__ agg,
+__global__ void __launch_bounds__(BT, 1) k_node_post_bwd(const float* __restrict__ h, const float* __restrict__ agg,
                                                            const float* __restrict__ z4, const float* __restrict__ dG,
                                                            int N, int nf, const float* __restrict__ W4,
                                                            const float* __restrict__ W4A, const float* __restrict__ W5,
                                                            float* __restrict__ dagg, float* __restrict__ dh,
                                                            float* __restrict__ partial) {
-    __shared__ __align__(16) float in_s[PT * DP];
-    __shared__ __align__(16) float dz_s[PT * ENF_H];
-    __shared__ float dg_s[PT * ENF_MAX_NF];
+    extern __shared__ __align__(16) float smem_np[];
+    float* in_s = smem_np;                       // [BPT][BDP]
+    float* dz_s = in_s + BPT * BDP;              // [BPT][H]
+    float* dg_s = dz_s + BPT * ENF_H;            // [BPT][MAX_NF]
+    float* wa_s = dg_s + BPT * ENF_MAX_NF;       // W4[:, nf:] as [k][jj], staged once per CTA
+    for (int idx = threadIdx.x; idx < ENF_H * ENF_H / 4; idx += BT)
+        reinterpret_cast<float4*>(wa_s)[idx] = __ldg(reinterpret_cast<const float4*>(W4A) + idx);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int D = nf + ENF_H;
     float wacc[4][JS];
@@ -98,13 +114,18 @@ __global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restric
         w5[c][0] = v.x; w5[c][1] = v.y; w5[c][2] = v.z; w5[c][3] = v.w;
         gw5[c][0] = gw5[c][1] = gw5[c][2] = gw5[c][3] = 0.f;
     }
-    float gb5 = 0.f;      // thread c < nf
-    const int tiles = (N + PT - 1) / PT;
+    float gb5 = 0.f;      // lane c < nf: partial over this warp's nodes
+    float w4h[ENF_MAX_NF][4];      // W4[4lane+c4][c] for the nf 'h' input columns (dh = W4[:, :nf]^T dz4)
+#pragma unroll
+    for (int c = 0; c < ENF_MAX_NF; ++c)
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) w4h[c][c4] = c < nf ? __ldg(W4 + (int64_t)(4 * lane + c4) * D + c) : 0.f;
+    const int tiles = (N + BPT - 1) / BPT;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int t0 = tile * PT;
+        const int t0 = tile * BPT;
         __syncthreads();
-        load_inputs(in_s, h, agg, t0, N, nf);
-        for (int idx = threadIdx.x; idx < PT * ENF_MAX_NF; idx += TPB) {
+        load_inputs<BPT, BDP, BT>(in_s, h, agg, t0, N, nf);
+        for (int idx = threadIdx.x; idx < BPT * ENF_MAX_NF; idx += BT) {
             const int t = idx / ENF_MAX_NF, c = idx % ENF_MAX_NF;
             dg_s[idx] = (t0 + t < N && c < nf) ? dG[(int64_t)(t0 + t) * nf + c] : 0.f;
         }
@@ -132,9 +153,17 @@ __global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restric
                 gb4[c4] += dz[c4];
             }
             *reinterpret_cast<float4*>(dz_s + (4 * w + t) * ENF_H + 4 * lane) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+            // dh[i][c] += sum_k W4[k][c] dz4[i][k]: lane-partial over its 4 hidden units, then a warp reduction
+#pragma unroll
+            for (int c = 0; c < ENF_MAX_NF; ++c) {
+                if (c < nf) {
+                    float pdh = fmaf(w4h[c][0], dz[0], fmaf(w4h[c][1], dz[1], fmaf(w4h[c][2], dz[2], w4h[c][3] * dz[3])));
+                    pdh = warp_sum(pdh);
+                    if (lane == 0 && i < N) dh[(int64_t)i * nf + c] += pdh;
+                }
+            }
+            if (lane < nf) gb5 += dg_s[(4 * w + t) * ENF_MAX_NF + lane];
         }
-        if (threadIdx.x < nf)
-            for (int t = 0; t < PT; ++t) gb5 += dg_s[t * ENF_MAX_NF + threadIdx.x];
         __syncthreads();
         // ---- dagg[i][jj] = sum_k W4A[k][jj] dz[i][k]; thread = 4 nodes x 4 jj
         {
@@ -144,7 +173,7 @@ __global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restric
             const float* dz0 = dz_s + (4 * w) * ENF_H;
 #pragma unroll 4
             for (int k = 0; k < ENF_H; ++k) {
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(W4A + (int64_t)k * ENF_H) + lane);
+                const float4 wv = *reinterpret_cast<const float4*>(wa_s + k * ENF_H + 4 * lane);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float d = dz0[t * ENF_H + k];
@@ -158,20 +187,11 @@ __global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restric
                 if (i < N) *reinterpret_cast<float4*>(dagg + (int64_t)i * ENF_H + 4 * lane) = make_float4(a[t][0], a[t][1], a[t][2], a[t][3]);
             }
         }
-        // ---- dh[i][c] += sum_k W4[k][c] dz[i][k]; thread = (node, c)
-        {
-            const int t = threadIdx.x >> 3, c = threadIdx.x & 7;
-            if (c < nf && t0 + t < N) {
-                float a = 0.f;
-                for (int k = 0; k < ENF_H; ++k) a = fmaf(__ldg(W4 + (int64_t)k * D + c), dz_s[t * ENF_H + k], a);
-                dh[(int64_t)(t0 + t) * nf + c] += a;
-            }
-        }
-        // ---- dW4[k][j] += sum_i dz[i][k] in[i][j]; thread = hidden 4lane..+3 x inputs 17w..17w+16
+        // ---- dW4[k][j] += sum_i dz[i][k] in[i][j]; thread = hidden 4lane..+3 x inputs 9w..9w+8
 #pragma unroll 2
-        for (int t = 0; t < PT; ++t) {
+        for (int t = 0; t < BPT; ++t) {
             const float4 dv = *reinterpret_cast<const float4*>(dz_s + t * ENF_H + 4 * lane);
-            const float* ip = in_s + t * DP + JS * w;
+            const float* ip = in_s + t * BDP + JS * w;
 #pragma unroll
             for (int jj = 0; jj < JS; ++jj) {
                 const float a = ip[jj];
@@ -191,7 +211,7 @@ __global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restric
         }
     // db4 and dW5 rows: combine the 8 node groups (warps) in fixed order, one row at a time through smem
     p += (int64_t)ENF_H * D;
-    float* red = dz_s;                 // [8 warps][128]
+    float* red = dz_s;                 // [16 warps][128]
     const int R = 1 + nf;
     for (int r = 0; r < R; ++r) {
         __syncthreads();
@@ -206,11 +226,18 @@ __global__ void __launch_bounds__(TPB, 1) k_node_post_bwd(const float* __restric
         __syncthreads();
         if (threadIdx.x < ENF_H) {
             float s = 0.f;
-            for (int ww = 0; ww < 8; ++ww) s += red[ww * ENF_H + threadIdx.x];
+            for (int ww = 0; ww < BT / 32; ++ww) s += red[ww * ENF_H + threadIdx.x];
             p[r * ENF_H + threadIdx.x] = s;          // db4 [H] then dW5 [nf][H]: the partial layout order
         }
     }
-    if (threadIdx.x < nf) p[R * ENF_H + threadIdx.x] = gb5;
+    __syncthreads();
+    if (lane < ENF_MAX_NF) red[w * ENF_MAX_NF + lane] = gb5;
+    __syncthreads();
+    if (threadIdx.x < nf) {
+        float s5 = 0.f;
+        for (int ww = 0; ww < BT / 32; ++ww) s5 += red[ww * ENF_MAX_NF + threadIdx.x];
+        p[R * ENF_H + threadIdx.x] = s5;
+    }
 }
 
 __global__ void k_node_post_reduce(const float* __restrict__ partial, int n_cta, int stride, int D, int nf, int o_w4,
@@ -243,14 +270,22 @@ int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const flo
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const PackOffsets p = enf_pack_offsets(nf);
-    enf_count_launch(), k_node_post_fwd<<<(N + PT - 1) / PT, TPB, 0, st>>>(h, agg, N, nf, packed + p.w4t, lp + o.off[P_B4],
-                                                                       lp + o.off[P_W5], lp + o.off[P_B5], z4, G);
+    const size_t smem = sizeof(float) * (DP * ENF_H + PT * DP);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_node_post_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    int grid = (N + PT - 1) / PT;
+    if (grid > 2 * enf_num_sms()) grid = 2 * enf_num_sms();
+    enf_count_launch(), k_node_post_fwd<<<grid, TPB, smem, st>>>(h, agg, N, nf, packed + p.w4t, lp + o.off[P_B4],
+                                                                 lp + o.off[P_W5], lp + o.off[P_B5], z4, G);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
 
 static int node_post_bwd_grid(int N) {
-    const int tiles = (N + PT - 1) / PT;
+    const int tiles = (N + BPT - 1) / BPT;
     const int cap = enf_num_sms();
     return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
@@ -267,7 +302,13 @@ int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const f
     const PackOffsets p = enf_pack_offsets(nf);
     const int grid = node_post_bwd_grid(N);
     const int D = nf + ENF_H;
-    enf_count_launch(), k_node_post_bwd<<<grid, TPB, 0, st>>>(h, agg, z4, dG, N, nf, lp + o.off[P_W4], packed + p.w4a,
+    const size_t smem = sizeof(float) * (BPT * BDP + BPT * ENF_H + BPT * ENF_MAX_NF + ENF_H * ENF_H);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_node_post_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    enf_count_launch(), k_node_post_bwd<<<grid, BT, smem, st>>>(h, agg, z4, dG, N, nf, lp + o.off[P_W4], packed + p.w4a,
                                                               lp + o.off[P_W5], dagg, dh, partial);
     const int stride = ENF_H * D + ENF_H + nf * ENF_H + nf;
     enf_count_launch(), k_node_post_reduce<<<(stride + 255) / 256, 256, 0, st>>>(
