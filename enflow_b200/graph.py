@@ -22,6 +22,9 @@ class GraphedTrainStep:
     def __init__(self, model, nll, optimizer, example, warmup=3, eps=None):
         if not example.pos.is_cuda:
             raise RuntimeError('GraphedTrainStep needs the example batch on the CUDA device')
+        if getattr(model, '_dp_group', None) is not None:
+            raise RuntimeError('GraphedTrainStep: capturing the data-parallel all-reduce is not supported; '
+                               'launch data-parallel steps eagerly')
         self.model, self.nll, self.optimizer = model, nll, optimizer
         # optional static ArgMax-noise buffer (refill it before a replay); default: torch.randn inside the graph
         self.eps = None if eps is None else eps.detach().to(example.pos.device, torch.float32).contiguous().clone()
