@@ -230,9 +230,8 @@ def main():
     # is captured once in a CUDA graph and replayed (enflow_b200.graph); --no-graph launches every kernel eagerly.
     L = _lib.lib()
     gstep, graph_note, launches_per_step = None, 'eager launches', None
-    # (with more than one rank the NCCL all-reduce sits inside the backward node; capturing it hung on this image, so
-    #  data-parallel runs launch eagerly: the host keeps ahead of a >10 ms step anyway)
-    if not generate and not args.no_graph and world == 1:
+    # (with more than one rank the NCCL all-reduce is not captured: two graphs with one eager all-reduce between them)
+    if not generate and not args.no_graph:
         try:
             from enflow_b200.graph import GraphedTrainStep
             L.enflow_launch_count(1)

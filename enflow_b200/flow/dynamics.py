@@ -69,7 +69,7 @@ class _FlowFn(torch.autograd.Function):
                                           p(b['box']), p(b['off']), p(ctx.eps), p(ctx.ws), ctx.nbytes, p(dh), p(dg),
                                           p(dpos), p(dvel), p(dldj), p(ctx.status), _lib.stream()))
         flow._release_workspace(ctx.ws)
-        if flow._dp_group is not None:           # data parallel: one all-reduce over the flat buffer
+        if flow._dp_group is not None and not flow._dp_defer:   # data parallel: one all-reduce over the flat buffer
             from ..parallel import allreduce_mean_
             allreduce_mean_(grads, flow._dp_group)
         views = flow.grad_views(grads)
@@ -83,6 +83,7 @@ class LFIntegrator(BaseFlow):
         self._ws_cache = None
         self._ws_busy = False
         self._dp_group = None
+        self._dp_defer = False      # True: the caller all-reduces flat_grads itself (GraphedTrainStep)
         self.check_status = True
         self.last_status = None
         # edge-MLP arithmetic: 'fp32' (FFMA pipe), 'fp32_tc' (tcgen05, bf16x3 operand split, fp32-accurate),

@@ -22,9 +22,6 @@ class GraphedTrainStep:
     def __init__(self, model, nll, optimizer, example, warmup=3, eps=None):
         if not example.pos.is_cuda:
             raise RuntimeError('GraphedTrainStep needs the example batch on the CUDA device')
-        if getattr(model, '_dp_group', None) is not None:
-            raise RuntimeError('GraphedTrainStep: capturing the data-parallel all-reduce is not supported; '
-                               'launch data-parallel steps eagerly')
         self.model, self.nll, self.optimizer = model, nll, optimizer
         # optional static ArgMax-noise buffer (refill it before a replay); default: torch.randn inside the graph
         self.eps = None if eps is None else eps.detach().to(example.pos.device, torch.float32).contiguous().clone()
@@ -51,9 +48,21 @@ class GraphedTrainStep:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
             pass
+        # Data parallel: the NCCL all-reduce is NOT captured.  Two graphs (everything up to the gradients; the
+        # optimizer) with one eager all-reduce of the flat gradient buffer between their replays.
+        self.dp = getattr(model, '_dp_group', None) is not None
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._step_body()
+        if self.dp:
+            model._dp_defer = True
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._grad_body()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self.optimizer.step()
+            model._dp_defer = False
+        else:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step_body()
         self.status = model.last_status
         model.check_status = self._check
 
@@ -63,11 +72,15 @@ class GraphedTrainStep:
         v._meta = d._meta
         return v
 
-    def _step_body(self):
+    def _grad_body(self):
         self.optimizer.zero_grad(set_to_none=True)
         out, ldj = self.model(self._view(), eps=self.eps)
         loss = self.nll(out, ldj)
         loss.backward()
+        return loss
+
+    def _step_body(self):
+        loss = self._grad_body()
         self.optimizer.step()
         return loss
 
@@ -85,6 +98,10 @@ class GraphedTrainStep:
         if batch is not None:
             self.load(batch)
         self.graph.replay()
+        if self.dp:
+            from .parallel import allreduce_mean_
+            allreduce_mean_(self.model.flat_grads, self.model._dp_group)
+            self.graph_opt.replay()
         return self.loss
 
     def overflowed(self):
