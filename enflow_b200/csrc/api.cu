@@ -100,6 +100,11 @@ int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts) {
     return (int64_t)L * eo.size + ao.size;
 }
 
+int enflow_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int* step,
+                     float lr, float beta1, float beta2, float eps, void* stream) {
+    return enf_adam_step(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, ST(stream));
+}
+
 int64_t enflow_edges_workspace_ints(int N) { return enf_edges_workspace_ints(N); }
 
 int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const float* r_cut, const int* mol_off,

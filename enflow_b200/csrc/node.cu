@@ -204,15 +204,20 @@ int enf_node_pre_fwd(const float* h, int N, int nf, const float* lp, float* P, f
     return ENF_OK;
 }
 
+static int node_pre_bwd_grid(int N) {      // fewer CTAs than the forward: every CTA leaves a partial to reduce
+    const int g = enf_node_grid(N), cap = enf_num_sms();
+    return g < cap ? g : cap;
+}
+
 int64_t enf_node_pre_partial_floats(int N, int nf) {
-    return (int64_t)enf_node_grid(N) * (ENF_H * (2 * nf + 1) + ENF_H + ENF_H * nf + ENF_H + ENF_H + 1);
+    return (int64_t)node_pre_bwd_grid(N) * (ENF_H * (2 * nf + 1) + ENF_H + ENF_H * nf + ENF_H + ENF_H + 1);
 }
 
 int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float* dP, const float* dS,
                      const float* dQ, float* dh, float* lgrad, float* partial, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
-    const int grid = enf_node_grid(N);
+    const int grid = node_pre_bwd_grid(N);
     enf_count_launch(), k_node_pre_bwd<<<grid, TPB, 0, st>>>(h, N, nf, lp + o.off[P_W1], lp + o.off[P_W6], lp + o.off[P_B6],
                                          lp + o.off[P_W7], dP, dS, dQ, dh, partial);
     SegTable s;

@@ -25,6 +25,7 @@ from .data.base import DataLoader
 from .flow.loss import Alchemical_NLL
 from .nn.argmax import ArgMax
 from .nn.egcl import EGCL
+from .optim import FlatAdam
 from .parallel import env_ranks, init_data_parallel
 from .utils.conversion import SIGMA_M, kelvin_to_lj, lj_to_kelvin, time_to_lj
 
@@ -122,7 +123,8 @@ class Main:
         tr = args['training']
         self.log_interval = int(tr['log_interval'])
         self.num_epochs = int(tr['num_epochs'])
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=float(tr['lr']))
+        # Adam as in main.py:177, as one fused kernel over the flat buffers; its state_dict has torch.optim.Adam's layout
+        self.optimizer = FlatAdam(self.model, lr=float(tr['lr']))
         self.scheduler = None
         if tr.get('scheduler'):
             step, gamma = float(tr['scheduler_step']), float(tr['gamma'])

@@ -64,6 +64,11 @@ int enflow_timing_read(float* ms, int* counts);
  * offsets/counts: host arrays of 15*L + 4 entries.  Returns the total buffer length in floats. */
 int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts);
 
+/* ---- optimizer step on the flat buffers (torch.optim.Adam in enflow/main.py:177,222): in-place Adam over n floats,
+ * step counter on the device (int[1], incremented by the call) so the launch is CUDA-graph capturable. */
+int enflow_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t* step,
+                     float lr, float beta1, float beta2, float eps, void* stream);
+
 /* ---- K0 neighbour list: Data.edges (enflow/data/base.py:122-144, utils/helpers.py:15-29) -------
  * pos/box are fp32 (pos_is_f64 = 0) or fp64 (1).  Output is grouped by row (CSR): row/col [E_cap],
  * rowptr [N+1]; ref_pos[e] (nullable) is the index the edge has in the reference's own ordering.
