@@ -188,9 +188,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             const float4 s = __ldg(reinterpret_cast<const float4*>(S + (int64_t)ti.col[m] * ENF_H) + lane);
             float x[4] = {fmaf(wr4.x, r, p.x + s.x), fmaf(wr4.y, r, p.y + s.y), fmaf(wr4.z, r, p.z + s.z),
                           fmaf(wr4.w, r, p.w + s.w)};
-            const bool ok = ti.valid[m];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = ok ? x[j] * tc::sigmoid_sfu(x[j]) : 0.f;
+            for (int j = 0; j < 4; ++j) x[j] = x[j] * tc::sigmoid_sfu(x[j]);      // padding rows: finite, masked in epilogue 1
             const uint32_t off = tc::img_chunk_offset(m, lane >> 1) + ((lane & 1) << 3);
             if (SPLIT) {
                 uint2 hi, lo;

@@ -103,7 +103,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     TileInfoB& ti = *reinterpret_cast<TileInfoB*>(sm + L::t_off);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
     uint64_t* bar_mma = bar_w + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+    uint64_t* bar_wg = bar_w + 2;          // the weight-gradient MMAs of a phase have completed (operands reusable)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = w & 3, cg = w >> 2;
@@ -113,6 +114,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     if (tid == 0) {
         tc::mbar_init(bar_w, 1);
         tc::mbar_init(bar_mma, 1);
+        tc::mbar_init(bar_wg, 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -161,24 +163,23 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int m = ec + 8 * ch + j;
-                const bool ok = ti.valid[m];
-                const float z = ok ? fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) +
-                                                          __ldg(S + (int64_t)ti.col[m] * ENF_H + n)) : 0.f;
+                const float z = fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) +
+                                                     __ldg(S + (int64_t)ti.col[m] * ENF_H + n));
                 const float sg = tc::sigmoid_sfu(z);
-                x[j] = ok ? z * sg : 0.f;
-                if (ds1) ds1[8 * ch + j] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;
+                x[j] = z * sg;
+                if (ds1) ds1[8 * ch + j] = fmaf(x[j], 1.0f - sg, sg);       // silu'(z) = s + z s (1 - s)
             }
             store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);
         }
     };
-    auto issue_mma = [&](auto&& body) {          // one thread issues
+    auto issue_mma = [&](auto&& body, bool commit = true) {          // one thread issues
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
             body();
-            tc::mma_commit(bar_mma);
+            if (commit) tc::mma_commit(bar_mma);
         }
     };
     auto wait_mma = [&]() {                      // everybody waits for completion
@@ -187,7 +188,15 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         tc::fence_after_sync();
     };
     auto run_mma = [&](auto&& body) { issue_mma(body); wait_mma(); };
+    uint32_t parity_wg = 0;
+    auto wait_wgrad = [&]() {                    // dgrad first, wgrad behind it: only operand reuse waits for the wgrad
+        tc::mbar_wait(bar_wg, parity_wg);
+        parity_wg ^= 1;
+    };
 
+    // Padding edges of the last tile are treated as self-edges of atom 0 with ds = 0 and dagg masked to 0: their
+    // activations are finite and every gradient quantity that touches them is exactly zero, so the epilogues carry
+    // no per-element validity selects (only stores and the dagg gather are predicated).
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int e0 = tile * TE;
         __syncthreads();
@@ -224,6 +233,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             ti.ddir[tid][0] = q0; ti.ddir[tid][1] = q1; ti.ddir[tid][2] = q2;
         }
         __syncthreads();
+        if (!first_tile) wait_wgrad();       // the previous tile's TW2 MMAs still read x1^T / dz2^T until here
         gen_x1(nullptr);
         // ---- T1 = W2 x1^T
         run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T1_COL, dW2k, WLO, dXTm, ALO, id_kmn64, false); });
@@ -236,11 +246,10 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int jj = 8 * ch + j;
-                    const bool ok = ti.valid[ec + jj];
                     const float z = dsl2[jj] + b2n;
                     const float sg = tc::sigmoid_sfu(z);
-                    x[j] = ok ? z * sg : 0.f;
-                    dsl2[jj] = ok ? sg * (1.0f + z * (1.0f - sg)) : 0.f;
+                    x[j] = z * sg;
+                    dsl2[jj] = fmaf(x[j], 1.0f - sg, sg);
                 }
                 store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);          // x2^T image [k][e] over x1^T
             }
@@ -259,8 +268,9 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                     const float z = v[jj] + b3n;
                     const float sg = tc::sigmoid_sfu(z);
                     const float ds = ti.ds[ec + jj];
-                    gwc = fmaf(ds, z * sg, gwc);
-                    const float dz = ds * wcn * (sg * (1.0f + z * (1.0f - sg)));
+                    const float x3 = z * sg;
+                    gwc = fmaf(ds, x3, gwc);
+                    const float dz = ds * wcn * fmaf(x3, 1.0f - sg, sg);
                     gb3 += dz;
                     x[j] = dz;
                 }
@@ -269,9 +279,11 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         }
         // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T   (while the tensor pipe runs: gather dagg)
         issue_mma([&]() {
-            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW3_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T2_COL, dW3m, WLO, dZm, ALO, id_mm64, false);
-        });
+            tc::mma_commit(bar_mma);             // the epilogue only needs the dgrad ...
+            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW3_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
+            tc::mma_commit(bar_wg);              // ... the wgrad finishes behind it
+        }, false);
         float da[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -281,15 +293,16 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             float v[16];
             tc::tmem_ld16(lane_base + T2_COL + ec, v);
 #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = (v[j] + da[j]) * dsl2[j];
+                gb2 += v[j];
+            }
+            wait_wgrad();                        // dz3^T / x2^T are still being read by the TW3 MMAs until here
+#pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 float x[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int jj = 8 * ch + j;
-                    const float dz = (v[jj] + da[jj]) * dsl2[jj];
-                    gb2 += dz;
-                    x[j] = dz;
-                }
+                for (int j = 0; j < 8; ++j) x[j] = v[8 * ch + j];
                 store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz2^T image [n][e]
             }
         }
@@ -297,9 +310,11 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         gen_x1(ds1);                                                    // x2^T is dead: rebuild x1^T, keep silu'(z1)
         // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   
         issue_mma([&]() {
-            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW2_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T1_COL, dW2m, WLO, dZm, ALO, id_mm64, false);
-        });
+            tc::mma_commit(bar_mma);
+            tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW2_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
+            tc::mma_commit(bar_wg);              // waited for at the top of the next tile (before x1^T is rebuilt)
+        }, false);
         first_tile = false;
         wait_mma();
         {
@@ -336,6 +351,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         }
     }
     // ---- per-CTA partials: weight gradients from TMEM, vector gradients combined over the 4 edge groups
+    if (!first_tile) wait_wgrad();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();

@@ -273,3 +273,17 @@ def test_tc_flow_train_step_vs_oracle(name, mode, tol, gtol):
     worst = sorted(((np.linalg.norm(to_np(p.grad) - ref_grads[k].numpy()) / max(np.linalg.norm(ref_grads[k].numpy()), 1e-300), k)
                     for k, p in model.named_parameters()), reverse=True)
     assert worst[0][0] < gtol, f'{mode} worst gradient errors: {worst[:5]}'
+
+
+def test_edge_capacity_overflow_is_detected_and_retried():
+    """A too-small edge capacity sets the device status flag; the host doubles the capacity and redoes the pass."""
+    c = load_case('c1_pbc')
+    model = build_model(c['sd'], c['nf'], c['L'], precision='fp32_tc')
+    data = gpu_batch(c['batch'])
+    B, N = int(c['batch']['N'].shape[0]), int(c['batch']['N'].sum())
+    model._edge_caps[(B, N)] = 128                      # far below the ~670 edges of this batch
+    with torch.no_grad():
+        out, ldj = model(data, eps=torch.as_tensor(c['eps']))
+    assert model._edge_caps[(B, N)] >= 1024
+    for k in ('h', 'g', 'pos', 'vel'):
+        assert rel_err(to_np(getattr(out, k)), c['gold'][f'out_{k}']) < FWD_TOL, k
