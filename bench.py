@@ -147,10 +147,13 @@ def main():
     ap.add_argument('--config', default='c2', choices=list(CONFIGS))
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precision', default='fp32_tc', choices=['fp32', 'fp32_tc', 'bf16'])
+    ap.add_argument('--precision', default=None, choices=['fp32', 'fp32_tc', 'bf16'],
+                    help='edge-MLP arithmetic; default: fp32_tc (fp32-accurate, tensor cores), bf16 for c5 as BASELINE.json asks')
     ap.add_argument('--no-graph', action='store_true', help='launch every step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.precision is None:
+        args.precision = 'bf16' if args.config == 'c5' else 'fp32_tc'
     if args.impl == 'reference':
         return run_reference(args)
 
