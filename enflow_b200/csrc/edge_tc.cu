@@ -290,13 +290,15 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 
 }  // namespace
 
-int64_t enf_tc_pack_bytes() { return 4 * (int64_t)tc::IMG_BYTES; }
+int64_t enf_tc_pack_bytes() { return tc::PACK_BYTES; }
+
+int enf_node_tc_pack(const float* lp, int nf, unsigned char* img, cudaStream_t st);
 
 int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t st) {
     const EgclOffsets o = enf_egcl_offsets(nf);
     enf_count_launch(), k_pack_tc<<<(2 * 128 * 16 + 255) / 256, 256, 0, st>>>(lp + o.off[P_W2], lp + o.off[P_W3], img);
     ENF_CHECK_LAUNCH();
-    return ENF_OK;
+    return enf_node_tc_pack(lp, nf, img, st);
 }
 
 // mode 1 = split (fp32-accurate), mode 2 = bf16

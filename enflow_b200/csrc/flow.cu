@@ -35,6 +35,7 @@ struct Bump {
 struct LayerSave {           // kept per layer when training
     int *row, *col, *rowptr, *E_dev, *mis;
     float *Q, *z2, *z3, *s, *agg, *z4;     // z2/z3 only in mode 0 (the tensor-core backward recomputes them)
+    float *P, *S;                          // node-level halves of edge_nn.0 (2 x N x H: cheaper to keep than to redo)
 };
 
 struct Workspace {
@@ -43,7 +44,7 @@ struct Workspace {
     LayerSave layer[16];
     float* packed;           // L * pack size
     unsigned char* tcimg;    // L * swizzled bf16 weight images for the tcgen05 kernels
-    float *P, *S, *F, *G, *trans, *wr, *runs;
+    float *F, *G, *trans, *wr, *runs;
     int* run_scratch;
     int* edges_ws;
     float* logq_atom;
@@ -84,10 +85,10 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
         s.z2 = d.mode == 0 ? b.take<float>(E * H) : nullptr;
         s.z3 = d.mode == 0 ? b.take<float>(E * H) : nullptr;
         s.agg = b.take<float>(N * H); s.z4 = b.take<float>(N * H);
+        s.P = b.take<float>(N * H); s.S = b.take<float>(N * H);
     }
     w.packed = b.take<float>((size_t)d.L * enf_pack_offsets(d.nf).size);
     w.tcimg = b.take<unsigned char>((size_t)d.L * enf_tc_pack_bytes() + 1024);
-    w.P = b.take<float>(N * H); w.S = b.take<float>(N * H);
     w.F = b.take<float>(N * 3); w.G = b.take<float>(N * nf);
     w.trans = b.take<float>(E * 3); w.wr = b.take<float>(H);
     w.runs = d.mode ? b.take<float>((size_t)enf_run_rows(d.E_cap, d.N) * H) : nullptr;
@@ -135,20 +136,23 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
                  int* status, cudaStream_t st) {
     TIMED(TK_EDGES, enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
                                      sv.E_dev, status, w.edges_ws, st));
-    TIMED(TK_NODE_PRE, enf_node_pre_fwd(h, d.N, d.nf, lp, w.P, w.S, sv.Q, st));
+    TIMED(TK_NODE_PRE, enf_node_pre_fwd(h, d.N, d.nf, lp, sv.P, sv.S, sv.Q, st));
     if (d.mode == 0) {
-        TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, packed, d.nf, w.wr,
+        TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, packed, d.nf, w.wr,
                                         sv.z2, sv.z3, sv.s, w.trans, st));
         TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
     } else {
         // tensor-core path: the kernel reduces silu(z2) over each row into per-run partials; no [E,H] store
         ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
-        TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, w.P, w.S, lp, tcimg, d.nf,
+        TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, tcimg, d.nf,
                                            sv.rowptr, sv.mis, w.runs, sv.s, w.trans, st));
         TIMED(TK_SEG128, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, sv.agg, st));
     }
     TIMED(TK_SEG3, enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
-    TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
+    if (d.mode == 0)
+        TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
+    else
+        TIMED(TK_NODE_POST, enf_node_post_fwd_tc(d.mode, h, sv.agg, d.N, d.nf, lp, tcimg, sv.z4, w.G, st));
     return ENF_OK;
 }
 
@@ -222,10 +226,13 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         // coupling step (dynamics.py:14-21): gradients w.r.t. Q, F, G and the incoming state
         TIMED(TK_COUPLING, enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
         // node_model (egcl.py:65-69)
-        TIMED(TK_NODE_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp,
-                                             w.packed + (int64_t)l * enf_pack_offsets(nf).size, w.dagg, dh, lg, w.partial, st));
-        // edge_model + force_model (egcl.py:57-63,71-75); P/S are recomputed, not stored
-        TIMED(TK_NODE_PRE, enf_node_pre_fwd(w.h[l], d.N, nf, lp, w.P, w.S, w.Qscratch, st));
+        if (d.mode == 0)
+            TIMED(TK_NODE_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp,
+                                                 w.packed + (int64_t)l * enf_pack_offsets(nf).size, w.dagg, dh, lg, w.partial, st));
+        else
+            TIMED(TK_NODE_BWD, enf_node_post_bwd_tc(d.mode, w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, tc_image(w, l), w.dagg,
+                                                    dh, lg, w.partial, st));
+        // edge_model + force_model (egcl.py:57-63,71-75); P/S were kept by the forward pass
         // column-grouped view of the edges; reused as is when this layer's list equals the one just processed
         // (fully connected regime: the neighbour list is the same at every coupling step)
         const int* skip = nullptr;
@@ -237,13 +244,13 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
                                               w.edges_ws, skip, st));
         if (d.mode == 0) {
-            TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P, w.S, lp, nf,
+            TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P, sv.S, lp, nf,
                                             w.wr, sv.z2, sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg,
                                             w.partial, st));
             TIMED(TK_SEG128, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
         } else {
-            TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, w.P,
-                                               w.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
+            TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
+                                               sv.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
                                                w.runs, w.dz1, w.dd, lg, w.partial, st));
             TIMED(TK_SEG128, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, st));
         }

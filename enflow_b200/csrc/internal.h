@@ -75,6 +75,12 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
                     const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
                     float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
                     float* partial, cudaStream_t st);
+// tensor-core node_model (node_tc.cu); weight images live behind the edge images in the same per-layer buffer
+int enf_node_post_fwd_tc(int mode, const float* h, const float* agg, int N, int nf, const float* lp,
+                         const unsigned char* wimg, float* z4, float* G, cudaStream_t st);
+int enf_node_post_bwd_tc(int mode, const float* h, const float* agg, const float* z4, const float* dG, int N, int nf,
+                         const float* lp, const unsigned char* wimg, float* dagg, float* dh, float* lgrad,
+                         float* partial, cudaStream_t st);
 // per-run partial segment sums (segment.cu): mis = N+2 ints, runs = enf_run_rows(E_cap, N) x 128 floats
 int64_t enf_scan_scratch_ints(int64_t n);
 int enf_run_index(const int* rowptr, int N, int* mis, int* scratch, cudaStream_t st);

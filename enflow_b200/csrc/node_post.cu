@@ -240,20 +240,29 @@ __global__ void __launch_bounds__(BT, 1) k_node_post_bwd(const float* __restrict
     }
 }
 
-__global__ void k_node_post_reduce(const float* __restrict__ partial, int n_cta, int stride, int D, int nf, int o_w4,
-                                   int o_b4, int o_w5, int o_b5, float* __restrict__ grad) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= stride) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // fixed order: four interleaved chains, combined at the end
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-        a0 += partial[(int64_t)(c + 0) * stride + idx];
-        a1 += partial[(int64_t)(c + 1) * stride + idx];
-        a2 += partial[(int64_t)(c + 2) * stride + idx];
-        a3 += partial[(int64_t)(c + 3) * stride + idx];
+// grad += sum over CTAs of the per-CTA partials; block = 32 elements x 8 CTA groups (group y adds CTAs y, y+8, ...
+// in order, then the eight group sums are added in order): deterministic and coalesced
+__global__ void __launch_bounds__(256) k_node_post_reduce(const float* __restrict__ partial, int n_cta, int stride, int D,
+                                                           int nf, int o_w4, int o_b4, int o_w5, int o_b5,
+                                                           float* __restrict__ grad) {
+    __shared__ float part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + tx;
+    float a0 = 0.f, a1 = 0.f;
+    if (idx < stride) {
+        int c = ty;
+        for (; c + 8 < n_cta; c += 16) {
+            a0 += partial[(int64_t)c * stride + idx];
+            a1 += partial[(int64_t)(c + 8) * stride + idx];
+        }
+        if (c < n_cta) a0 += partial[(int64_t)c * stride + idx];
     }
-    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * stride + idx];
-    const float acc = (a0 + a1) + (a2 + a3);
+    part[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty != 0 || idx >= stride) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) acc += part[y][tx];
     const int s0 = ENF_H * D, s1 = s0 + ENF_H, s2 = s1 + nf * ENF_H;
     int dst;
     if (idx < s0) dst = o_w4 + idx;
@@ -284,6 +293,16 @@ int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const flo
     return ENF_OK;
 }
 
+int enf_node_post_reduce(const float* partial, int n_cta, int nf, float* lgrad, cudaStream_t st) {
+    const EgclOffsets o = enf_egcl_offsets(nf);
+    const int D = nf + ENF_H;
+    const int stride = ENF_H * D + ENF_H + nf * ENF_H + nf;
+    enf_count_launch(), k_node_post_reduce<<<(stride + 31) / 32, 256, 0, st>>>(
+        partial, n_cta, stride, D, nf, (int)o.off[P_W4], (int)o.off[P_B4], (int)o.off[P_W5], (int)o.off[P_B5], lgrad);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
 static int node_post_bwd_grid(int N) {
     const int tiles = (N + BPT - 1) / BPT;
     const int cap = enf_num_sms();
@@ -301,7 +320,6 @@ int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const f
     const EgclOffsets o = enf_egcl_offsets(nf);
     const PackOffsets p = enf_pack_offsets(nf);
     const int grid = node_post_bwd_grid(N);
-    const int D = nf + ENF_H;
     const size_t smem = sizeof(float) * (BPT * BDP + BPT * ENF_H + BPT * ENF_MAX_NF + ENF_H * ENF_H);
     static bool attr = false;
     if (!attr) {
@@ -310,9 +328,6 @@ int enf_node_post_bwd(const float* h, const float* agg, const float* z4, const f
     }
     enf_count_launch(), k_node_post_bwd<<<grid, BT, smem, st>>>(h, agg, z4, dG, N, nf, lp + o.off[P_W4], packed + p.w4a,
                                                               lp + o.off[P_W5], dagg, dh, partial);
-    const int stride = ENF_H * D + ENF_H + nf * ENF_H + nf;
-    enf_count_launch(), k_node_post_reduce<<<(stride + 255) / 256, 256, 0, st>>>(
-        partial, grid, stride, D, nf, (int)o.off[P_W4], (int)o.off[P_B4], (int)o.off[P_W5], (int)o.off[P_B5], lgrad);
     ENF_CHECK_LAUNCH();
-    return ENF_OK;
+    return enf_node_post_reduce(partial, grid, nf, lgrad, st);
 }

@@ -15,6 +15,14 @@ constexpr int TILE = 128;
 constexpr int BLK_BYTES = 128 * 128;          // one 64-column block of a 128-row tile
 constexpr int IMG_BYTES = 2 * BLK_BYTES;      // 128 x 128 bf16
 
+// Per-layer weight image buffer (bytes): the edge kernels' W2 hi, W2 lo, W3 hi, W3 lo, then the node kernels'
+// images (node_tc.cu), each as hi followed by lo.
+constexpr int NODE_W4A = 4 * IMG_BYTES;                  // node_nn.0.weight[:, nf:]  [k][jj]      2 x 32 KB
+constexpr int NODE_W4H = NODE_W4A + 2 * IMG_BYTES;       // node_nn.0.weight[:, :nf]^T [c 16][k]   2 x 4 KB
+constexpr int NODE_W4F = NODE_W4H + 2 * 4096;            // node_nn.0.weight [k][agg | h | pad 192] 2 x 48 KB
+constexpr int NODE_W5 = NODE_W4F + 2 * 3 * BLK_BYTES;    // node_nn.2.weight [c 16][k]             2 x 4 KB
+constexpr int PACK_BYTES = NODE_W5 + 2 * 4096;
+
 // byte offset of the 16-byte chunk holding columns [8*chunk16, 8*chunk16+8) of `row`
 __host__ __device__ inline uint32_t img_chunk_offset(int row, int chunk16) {
     const int blk = chunk16 >> 3, c = chunk16 & 7;
