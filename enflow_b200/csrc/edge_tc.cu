@@ -40,7 +40,7 @@ struct Smem {
     static constexpr size_t a_off = (size_t)NW * tc::IMG_BYTES;
     static constexpr size_t c_off = a_off + (size_t)NA * tc::IMG_BYTES;
     static constexpr size_t t_off = c_off + sizeof(Consts);
-    static constexpr size_t bar_off = (t_off + sizeof(TileInfo) + 15) / 16 * 16;
+    static constexpr size_t bar_off = (t_off + 2 * sizeof(TileInfo) + 15) / 16 * 16;    // double-buffered tile info
     static constexpr size_t total = bar_off + 64 + 1024;   // + alignment slack
 };
 
@@ -113,7 +113,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     unsigned char* sm = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
     unsigned char* Wimg = sm + L::w_off;
     unsigned char* A = sm + L::a_off;
-    TileInfo& ti = *reinterpret_cast<TileInfo*>(sm + L::t_off);
+    TileInfo* tib = reinterpret_cast<TileInfo*>(sm + L::t_off);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
     uint64_t* bar_mma = bar_w + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
@@ -158,9 +158,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 
     const int E = E_dev[0];
     const int tiles = (E + tc::TILE - 1) / tc::TILE;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int e0 = tile * tc::TILE;
-        if (tid < tc::TILE) {       // edge geometry (data/base.py:15-19, egcl.py:80)
+    auto geometry = [&](TileInfo& ti, int e0) {       // edge geometry (data/base.py:15-19, egcl.py:80)
+        if (tid < tc::TILE) {
             const int e = e0 + tid;
             const bool ok = e < E;
             int i = 0, j = 0;
@@ -177,19 +176,28 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             ti.d[tid][0] = d0; ti.d[tid][1] = d1; ti.d[tid][2] = d2;
             ti.r[tid] = d0 * d0 + d1 * d1 + d2 * d2;
         }
-        __syncthreads();
-        // ---- x1 = silu(P[row] + S[col] + w_r r): one warp per edge row, lanes = 4 consecutive features
-        //      (coalesced 512-byte row reads), written into the K-major [edge][feature] operand image
-#pragma unroll 2
+    };
+    // z1 = P[row] + S[col] + w_r r: one warp per edge row, lanes = 4 consecutive features (coalesced 512-byte
+    // row reads); gathered one tile ahead (behind the second MMA of the previous tile) and kept in registers
+    auto load_z1 = [&](const TileInfo& ti, float (&z)[tc::TILE / 16][4]) {
+#pragma unroll
         for (int it = 0; it < tc::TILE / 16; ++it) {
             const int m = w + 16 * it;
             const float r = ti.r[m];
             const float4 p = __ldg(reinterpret_cast<const float4*>(P + (int64_t)ti.row[m] * ENF_H) + lane);
             const float4 s = __ldg(reinterpret_cast<const float4*>(S + (int64_t)ti.col[m] * ENF_H) + lane);
-            float x[4] = {fmaf(wr4.x, r, p.x + s.x), fmaf(wr4.y, r, p.y + s.y), fmaf(wr4.z, r, p.z + s.z),
-                          fmaf(wr4.w, r, p.w + s.w)};
+            z[it][0] = fmaf(wr4.x, r, p.x + s.x); z[it][1] = fmaf(wr4.y, r, p.y + s.y);
+            z[it][2] = fmaf(wr4.z, r, p.z + s.z); z[it][3] = fmaf(wr4.w, r, p.w + s.w);
+        }
+    };
+    // x1 = silu(z1) into the K-major [edge][feature] operand image
+    auto put_x1 = [&](const float (&z)[tc::TILE / 16][4]) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = x[j] * tc::sigmoid_sfu(x[j]);      // padding rows: finite, masked in epilogue 1
+        for (int it = 0; it < tc::TILE / 16; ++it) {
+            const int m = w + 16 * it;
+            float x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = z[it][j] * tc::sigmoid_sfu(z[it][j]);      // padding rows: finite, masked in epilogue 1
             const uint32_t off = tc::img_chunk_offset(m, lane >> 1) + ((lane & 1) << 3);
             if (SPLIT) {
                 uint2 hi, lo;
@@ -201,6 +209,20 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                 *reinterpret_cast<uint2*>(A + off) = make_uint2(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]));
             }
         }
+    };
+    // Software pipeline over the CTA's tiles: geometry of tile t+1 behind the first MMA of tile t, its z1 gather
+    // behind the second.
+    int cur = 0;
+    float z1[tc::TILE / 16][4];
+    if ((int)blockIdx.x < tiles) geometry(tib[0], blockIdx.x * tc::TILE);
+    __syncthreads();
+    if ((int)blockIdx.x < tiles) load_z1(tib[0], z1);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * tc::TILE;
+        TileInfo& ti = tib[cur];
+        TileInfo& tn = tib[cur ^ 1];
+        const int next = tile + gridDim.x;
+        put_x1(z1);
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {             // z2^T = W2 x1^T on the tensor core
@@ -209,6 +231,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffK128>(tmem, dW2, tc::IMG_BYTES, dXk, tc::IMG_BYTES, idesc_kk, false);
             tc::mma_commit(bar_mma);
         }
+        if (next < tiles) geometry(tn, next * tc::TILE);
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
@@ -258,6 +281,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem, dW3, tc::IMG_BYTES, dXmn, tc::IMG_BYTES, idesc_kmn, false);
             tc::mma_commit(bar_mma);
         }
+        if (next < tiles) load_z1(tn, z1);
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
@@ -281,7 +305,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int c = 0; c < 3; ++c) trans[(int64_t)e * 3 + c] = fminf(fmaxf(ti.d[tid][c] * s, -100.f), 100.f);
         }
-        __syncthreads();
+        cur ^= 1;          // the other TileInfo is next; this one is rewritten only after the next pre-MMA barrier
     }
     tc::fence_before_sync();
     __syncthreads();

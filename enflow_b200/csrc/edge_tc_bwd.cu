@@ -38,7 +38,7 @@ struct SmemB {
     static constexpr size_t x_off = (size_t)NW * tc::IMG_BYTES;
     static constexpr size_t z_off = x_off + (size_t)NA * ACT_IMG;
     static constexpr size_t t_off = z_off + (size_t)NA * ACT_IMG;
-    static constexpr size_t bar_off = (t_off + sizeof(TileInfoB) + 15) / 16 * 16;
+    static constexpr size_t bar_off = (t_off + 2 * sizeof(TileInfoB) + 15) / 16 * 16;      // double-buffered tile info
     static constexpr size_t total = bar_off + 64 + 1024;
 };
 
@@ -100,7 +100,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     unsigned char* Wimg = sm + L::w_off;
     unsigned char* XB = sm + L::x_off;         // x1 image [e][k], later x2^T image [k][e], later x1 again
     unsigned char* ZB = sm + L::z_off;         // dz3^T then dz2^T image [n][e]
-    TileInfoB& ti = *reinterpret_cast<TileInfoB*>(sm + L::t_off);
+    TileInfoB* tib = reinterpret_cast<TileInfoB*>(sm + L::t_off);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
     uint64_t* bar_mma = bar_w + 1;
     uint64_t* bar_wg = bar_w + 2;          // the weight-gradient MMAs of a phase have completed (operands reusable)
@@ -149,22 +149,27 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     uint32_t parity = 0;
     float gb2 = 0.f, gb3 = 0.f, gwc = 0.f, gwr = 0.f;
     bool first_tile = true;
-
     const int E = E_dev[0];
     const int tiles = (E + TE - 1) / TE;
 
-    // x1^T = silu(P[row] + S[col] + w_r r)^T into XB as the [hidden][edge] image, by the same (hidden unit,
-    // 16 edges) threads that run the epilogues (row reads coalesce over the 32 hidden units of a warp);
-    // ds1 != nullptr also returns silu'(z1) for the last epilogue
-    auto gen_x1 = [&](float* ds1) {
+    // z1 = P[row] + S[col] + w_r r for this thread's (hidden unit, 16 edges); row reads coalesce over the 32 hidden
+    // units of a warp.  The values stay in registers for the whole tile (x1^T is needed twice) and are gathered
+    // one tile ahead, behind the last MMA of the previous tile.
+    auto load_z1 = [&](const TileInfoB& ti, float (&z)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int m = ec + j;
+            z[j] = fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) + __ldg(S + (int64_t)ti.col[m] * ENF_H + n));
+        }
+    };
+    // x1^T = silu(z1)^T into XB as the [hidden][edge] image; ds1 != nullptr also returns silu'(z1)
+    auto put_x1 = [&](const float (&z1)[16], float* ds1) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             float x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int m = ec + 8 * ch + j;
-                const float z = fmaf(wrn, ti.r[m], __ldg(P + (int64_t)ti.row[m] * ENF_H + n) +
-                                                     __ldg(S + (int64_t)ti.col[m] * ENF_H + n));
+                const float z = z1[8 * ch + j];
                 const float sg = tc::sigmoid_sfu(z);
                 x[j] = z * sg;
                 if (ds1) ds1[8 * ch + j] = fmaf(x[j], 1.0f - sg, sg);       // silu'(z) = s + z s (1 - s)
@@ -172,34 +177,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);
         }
     };
-    auto issue_mma = [&](auto&& body, bool commit = true) {          // one thread issues
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            body();
-            if (commit) tc::mma_commit(bar_mma);
-        }
-    };
-    auto wait_mma = [&]() {                      // everybody waits for completion
-        tc::mbar_wait(bar_mma, parity);
-        parity ^= 1;
-        tc::fence_after_sync();
-    };
-    auto run_mma = [&](auto&& body) { issue_mma(body); wait_mma(); };
-    uint32_t parity_wg = 0;
-    auto wait_wgrad = [&]() {                    // dgrad first, wgrad behind it: only operand reuse waits for the wgrad
-        tc::mbar_wait(bar_wg, parity_wg);
-        parity_wg ^= 1;
-    };
-
-    // Padding edges of the last tile are treated as self-edges of atom 0 with ds = 0 and dagg masked to 0: their
-    // activations are finite and every gradient quantity that touches them is exactly zero, so the epilogues carry
-    // no per-element validity selects (only stores and the dagg gather are predicated).
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int e0 = tile * TE;
-        __syncthreads();
+    // per-edge geometry and the force-branch seed of one tile, by the first TE threads
+    auto geometry = [&](TileInfoB& ti, int e0) {
         if (tid < TE) {
             const int e = e0 + tid;
             const bool ok = e < E;
@@ -232,11 +211,50 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             ti.ds[tid] = ds;
             ti.ddir[tid][0] = q0; ti.ddir[tid][1] = q1; ti.ddir[tid][2] = q2;
         }
+    };
+    auto issue_mma = [&](auto&& body, bool commit = true) {          // one thread issues
+        tc::fence_async_smem();
+        tc::fence_before_sync();
         __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            body();
+            if (commit) tc::mma_commit(bar_mma);
+        }
+    };
+    auto wait_mma = [&]() {                      // everybody waits for completion
+        tc::mbar_wait(bar_mma, parity);
+        parity ^= 1;
+        tc::fence_after_sync();
+    };
+    auto run_mma = [&](auto&& body) { issue_mma(body); wait_mma(); };
+    uint32_t parity_wg = 0;
+    auto wait_wgrad = [&]() {                    // dgrad first, wgrad behind it: only operand reuse waits for the wgrad
+        tc::mbar_wait(bar_wg, parity_wg);
+        parity_wg ^= 1;
+    };
+
+    // Padding edges of the last tile are treated as self-edges of atom 0 with ds = 0 and dagg masked to 0: their
+    // activations are finite and every gradient quantity that touches them is exactly zero, so the epilogues carry
+    // no per-element validity selects (only stores and the dagg gather are predicated).
+    // Software pipeline over the CTA's tiles: the geometry of tile t+1 is computed behind the first MMA of tile t and
+    // its z1 gather is issued behind the last one, so neither latency is exposed.
+    int cur = 0;
+    float z1[16];
+    if ((int)blockIdx.x < tiles) geometry(tib[0], blockIdx.x * TE);
+    __syncthreads();
+    if ((int)blockIdx.x < tiles) load_z1(tib[0], z1);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * TE;
+        TileInfoB& ti = tib[cur];
+        TileInfoB& tn = tib[cur ^ 1];
+        const int next = tile + gridDim.x;
         if (!first_tile) wait_wgrad();       // the previous tile's TW2 MMAs still read x1^T / dz2^T until here
-        gen_x1(nullptr);
+        put_x1(z1, nullptr);
         // ---- T1 = W2 x1^T
-        run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T1_COL, dW2k, WLO, dXTm, ALO, id_kmn64, false); });
+        issue_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T1_COL, dW2k, WLO, dXTm, ALO, id_kmn64, false); });
+        if (next < tiles) geometry(tn, next * TE);
+        wait_mma();
         float dsl2[16];                 // silu'(z2), consumed two phases later
         {
             tc::tmem_ld16(lane_base + T1_COL + ec, dsl2);
@@ -307,7 +325,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             }
         }
         float ds1[16];
-        gen_x1(ds1);                                                    // x2^T is dead: rebuild x1^T, keep silu'(z1)
+        put_x1(z1, ds1);                                                // x2^T is dead: rebuild x1^T, keep silu'(z1)
         // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   
         issue_mma([&]() {
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T1_COL, dW2m, WLO, dZm, ALO, id_mm64, false);
@@ -316,6 +334,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             tc::mma_commit(bar_wg);              // waited for at the top of the next tile (before x1^T is rebuilt)
         }, false);
         first_tile = false;
+        if (next < tiles) load_z1(tn, z1);                              // next tile's gather, behind the MMAs
         wait_mma();
         {
             float v[16];
@@ -349,6 +368,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int c = 0; c < 3; ++c) dd_out[(int64_t)(e0 + tid) * 3 + c] = fmaf(dr2, ti.d[tid][c], ti.ddir[tid][c]);
         }
+        cur ^= 1;
     }
     // ---- per-CTA partials: weight gradients from TMEM, vector gradients combined over the 4 edge groups
     if (!first_tile) wait_wgrad();
