@@ -40,7 +40,7 @@ struct Smem {
     static constexpr size_t a_off = (size_t)NW * tc::IMG_BYTES;
     static constexpr size_t c_off = a_off + (size_t)NA * tc::IMG_BYTES;
     static constexpr size_t t_off = c_off + sizeof(Consts);
-    static constexpr size_t bar_off = (t_off + 2 * sizeof(TileInfo) + 15) / 16 * 16;    // double-buffered tile info
+    static constexpr size_t bar_off = (t_off + 3 * sizeof(TileInfo) + 15) / 16 * 16;    // tile info: three tiles in flight
     static constexpr size_t total = bar_off + 64 + 1024;   // + alignment slack
 };
 
@@ -116,7 +116,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     TileInfo* tib = reinterpret_cast<TileInfo*>(sm + L::t_off);
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
     uint64_t* bar_mma = bar_w + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+    uint64_t* bar_g1 = bar_w + 2;          // the first GEMM of a tile is issued one tile ahead: its own barrier
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = w & 3, cg = w >> 2;
@@ -126,10 +127,11 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     if (tid == 0) {
         tc::mbar_init(bar_w, 1);
         tc::mbar_init(bar_mma, 1);
+        tc::mbar_init(bar_g1, 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
-    if (w == 0) tc::tmem_alloc(tmem_slot, 128);
+    if (w == 0) tc::tmem_alloc(tmem_slot, 256);
     const float b2n = b2[n], b3n = b3[n], wcn = wc[n];
     const float4 wr4 = make_float4(W1[(4 * lane + 0) * e1 + e1 - 1], W1[(4 * lane + 1) * e1 + e1 - 1],
                                    W1[(4 * lane + 2) * e1 + e1 - 1], W1[(4 * lane + 3) * e1 + e1 - 1]);
@@ -153,8 +155,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     const uint64_t dXk = tc::make_desc(x_base, 16, 1024), dXmn = tc::make_desc(x_base, tc::BLK_BYTES, 1024);
     const uint32_t idesc_kk = tc::make_idesc(false, false);
     const uint32_t idesc_kmn = tc::make_idesc(false, true);
-    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)ec;
-    uint32_t parity = 0;
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)ec;     // z2 accumulator; z3 is 128 columns further
+    uint32_t parity = 0, parity_g1 = 0;
 
     const int E = E_dev[0];
     const int tiles = (E + tc::TILE - 1) / tc::TILE;
@@ -210,30 +212,39 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             }
         }
     };
-    // Software pipeline over the CTA's tiles: geometry of tile t+1 behind the first MMA of tile t, its z1 gather
-    // behind the second.
+    // Software pipeline over the CTA's tiles (t, t+1, t+2 = this CTA's consecutive tiles):
+    //   geometry(t+2) and the z1 gather of t+1 run behind the second MMA of tile t;
+    //   x1(t+1) is written and its first MMA issued (into the other accumulator) before epilogue 2 of tile t,
+    //   so that MMA runs under the epilogue instead of in front of an idle CTA.
+    auto issue_g1 = [&]() {          // z2^T[n][e] = sum_k W2[n][k] x1[e][k]: A = weight image, B = x1 image, both K-major
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffK128>(tmem, dW2, tc::IMG_BYTES, dXk, tc::IMG_BYTES, idesc_kk, false);
+            tc::mma_commit(bar_g1);
+        }
+    };
     int cur = 0;
     float z1[tc::TILE / 16][4];
-    if ((int)blockIdx.x < tiles) geometry(tib[0], blockIdx.x * tc::TILE);
-    __syncthreads();
-    if ((int)blockIdx.x < tiles) load_z1(tib[0], z1);
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int stride = gridDim.x;
+    if ((int)blockIdx.x < tiles) {
+        geometry(tib[0], blockIdx.x * tc::TILE);
+        if ((int)blockIdx.x + stride < tiles) geometry(tib[1], (blockIdx.x + stride) * tc::TILE);
+        __syncthreads();
+        load_z1(tib[0], z1);
+        put_x1(z1);
+        issue_g1();
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += stride) {
         const int e0 = tile * tc::TILE;
         TileInfo& ti = tib[cur];
-        TileInfo& tn = tib[cur ^ 1];
-        const int next = tile + gridDim.x;
-        put_x1(z1);
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {             // z2^T = W2 x1^T on the tensor core
-            tc::fence_after_sync();
-            // z2^T[n][e] = sum_k W2[n][k] x1[e][k]: A = weight image, B = x1 image, both K-major
-            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffK128>(tmem, dW2, tc::IMG_BYTES, dXk, tc::IMG_BYTES, idesc_kk, false);
-            tc::mma_commit(bar_mma);
-        }
-        if (next < tiles) geometry(tn, next * tc::TILE);
-        tc::mbar_wait(bar_mma, parity);
-        parity ^= 1;
+        TileInfo& tn = tib[cur == 2 ? 0 : cur + 1];
+        TileInfo& tnn = tib[cur == 0 ? 2 : cur - 1];
+        const int next = tile + stride, next2 = next + stride;
+        tc::mbar_wait(bar_g1, parity_g1);
+        parity_g1 ^= 1;
         tc::fence_after_sync();
         // ---- epilogue 1: bias, x2^T = silu(z2)^T as the next operand, and the segment sums of x2 over each
         //      row (egcl.py:66) as per-run partials: this thread owns hidden unit n for 32 consecutive edges, so
@@ -278,17 +289,22 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         if (tid == 0) {             // z3^T = W3 x2^T  (B read MN-major)
             tc::fence_after_sync();
             // z3^T = W3 x2^T: B is the [hidden][edge] image the epilogue wrote, read MN-major
-            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem, dW3, tc::IMG_BYTES, dXmn, tc::IMG_BYTES, idesc_kmn, false);
+            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + 128, dW3, tc::IMG_BYTES, dXmn, tc::IMG_BYTES, idesc_kmn, false);
             tc::mma_commit(bar_mma);
         }
+        if (next2 < tiles) geometry(tnn, next2 * tc::TILE);
         if (next < tiles) load_z1(tn, z1);
         tc::mbar_wait(bar_mma, parity);
         parity ^= 1;
         tc::fence_after_sync();
+        if (next < tiles) {          // the operand buffer is free again: next tile's x1 and first MMA
+            put_x1(z1);
+            issue_g1();
+        }
         // ---- epilogue 2: bias, s[e] = sum_n wc[n] silu(z3[e][n]) (transpose-reduce over the warp's 32 n)
         {
             float v[32];
-            tc::tmem_ld32(taddr, v);
+            tc::tmem_ld32(taddr + 128, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 v[j] += b3n;
@@ -305,11 +321,11 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int c = 0; c < 3; ++c) trans[(int64_t)e * 3 + c] = fminf(fmaxf(ti.d[tid][c] * s, -100.f), 100.f);
         }
-        cur ^= 1;          // the other TileInfo is next; this one is rewritten only after the next pre-MMA barrier
+        cur = cur == 2 ? 0 : cur + 1;
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (w == 0) tc::tmem_dealloc(tmem, 128);
+    if (w == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace
