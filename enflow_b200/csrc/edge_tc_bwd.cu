@@ -22,7 +22,7 @@ namespace {
 constexpr int THREADS = 512;
 constexpr int TE = 64;                     // edges per tile
 constexpr int ACT_IMG = 128 * TE * 2;      // one bf16 activation image: 16 KB
-constexpr uint32_t T1_COL = 0, T2_COL = 64, TW2_COL = 128, TW3_COL = 256, TMEM_COLS = 512;
+constexpr uint32_t T1_COL = 0, T2_COL = 64, TW2_COL = 128, TW3_COL = 256, T1B_COL = 384, TMEM_COLS = 512;   // T1 alternates per tile
 
 struct TileInfoB {
     int row[TE], col[TE], valid[TE], start[TE], mis[TE];
@@ -38,7 +38,7 @@ struct SmemB {
     static constexpr size_t x_off = (size_t)NW * tc::IMG_BYTES;
     static constexpr size_t z_off = x_off + (size_t)NA * ACT_IMG;
     static constexpr size_t t_off = z_off + (size_t)NA * ACT_IMG;
-    static constexpr size_t bar_off = (t_off + 2 * sizeof(TileInfoB) + 15) / 16 * 16;      // double-buffered tile info
+    static constexpr size_t bar_off = (t_off + 3 * sizeof(TileInfoB) + 15) / 16 * 16;      // tile info: three tiles in flight
     static constexpr size_t total = bar_off + 64 + 1024;
 };
 
@@ -104,7 +104,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(sm + L::bar_off);
     uint64_t* bar_mma = bar_w + 1;
     uint64_t* bar_wg = bar_w + 2;          // the weight-gradient MMAs of a phase have completed (operands reusable)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+    uint64_t* bar_g1 = bar_w + 3;          // the first GEMM of a tile is issued one tile ahead: its own barrier
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = w & 3, cg = w >> 2;
@@ -115,6 +116,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         tc::mbar_init(bar_w, 1);
         tc::mbar_init(bar_mma, 1);
         tc::mbar_init(bar_wg, 1);
+        tc::mbar_init(bar_g1, 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -227,7 +229,6 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         parity ^= 1;
         tc::fence_after_sync();
     };
-    auto run_mma = [&](auto&& body) { issue_mma(body); wait_mma(); };
     uint32_t parity_wg = 0;
     auto wait_wgrad = [&]() {                    // dgrad first, wgrad behind it: only operand reuse waits for the wgrad
         tc::mbar_wait(bar_wg, parity_wg);
@@ -237,27 +238,41 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     // Padding edges of the last tile are treated as self-edges of atom 0 with ds = 0 and dagg masked to 0: their
     // activations are finite and every gradient quantity that touches them is exactly zero, so the epilogues carry
     // no per-element validity selects (only stores and the dagg gather are predicated).
-    // Software pipeline over the CTA's tiles: the geometry of tile t+1 is computed behind the first MMA of tile t and
-    // its z1 gather is issued behind the last one, so neither latency is exposed.
+    // Software pipeline over the CTA's tiles (t, t+1, t+2 = this CTA's consecutive tiles):
+    //   geometry(t+2) is computed behind the second MMA of tile t, the z1 gather of t+1 behind the last one;
+    //   x1^T(t+1) is written and T1(t+1) = W2 x1^T issued (into the other T1 accumulator) before the last epilogue
+    //   of tile t, so that MMA runs under the epilogue.
+    uint32_t t1col = T1_COL, parity_g1 = 0;
+    auto issue_g1 = [&](uint32_t col) {
+        issue_mma([&]() {
+            tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + col, dW2k, WLO, dXTm, ALO, id_kmn64, false);
+            tc::mma_commit(bar_g1);
+        }, false);
+    };
     int cur = 0;
     float z1[16];
-    if ((int)blockIdx.x < tiles) geometry(tib[0], blockIdx.x * TE);
-    __syncthreads();
-    if ((int)blockIdx.x < tiles) load_z1(tib[0], z1);
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int stride = gridDim.x;
+    if ((int)blockIdx.x < tiles) {
+        geometry(tib[0], blockIdx.x * TE);
+        if ((int)blockIdx.x + stride < tiles) geometry(tib[1], (blockIdx.x + stride) * TE);
+        __syncthreads();
+        load_z1(tib[0], z1);
+        put_x1(z1, nullptr);
+        issue_g1(t1col);
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += stride) {
         const int e0 = tile * TE;
         TileInfoB& ti = tib[cur];
-        TileInfoB& tn = tib[cur ^ 1];
-        const int next = tile + gridDim.x;
-        if (!first_tile) wait_wgrad();       // the previous tile's TW2 MMAs still read x1^T / dz2^T until here
-        put_x1(z1, nullptr);
-        // ---- T1 = W2 x1^T
-        issue_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T1_COL, dW2k, WLO, dXTm, ALO, id_kmn64, false); });
-        if (next < tiles) geometry(tn, next * TE);
-        wait_mma();
+        TileInfoB& tn = tib[cur == 2 ? 0 : cur + 1];
+        TileInfoB& tnn = tib[cur == 0 ? 2 : cur - 1];
+        const int next = tile + stride, next2 = next + stride;
+        // ---- T1 = W2 x1^T (issued one tile ahead)
+        tc::mbar_wait(bar_g1, parity_g1);
+        parity_g1 ^= 1;
+        tc::fence_after_sync();
         float dsl2[16];                 // silu'(z2), consumed two phases later
         {
-            tc::tmem_ld16(lane_base + T1_COL + ec, dsl2);
+            tc::tmem_ld16(lane_base + t1col + ec, dsl2);
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 float x[8];
@@ -273,7 +288,9 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             }
         }
         // ---- T2 = W3 x2^T
-        run_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T2_COL, dW3k, WLO, dXTm, ALO, id_kmn64, false); });
+        issue_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T2_COL, dW3k, WLO, dXTm, ALO, id_kmn64, false); });
+        if (next2 < tiles) geometry(tnn, next2 * TE);
+        wait_mma();
         {
             float v[16];
             tc::tmem_ld16(lane_base + T2_COL + ec, v);
@@ -328,17 +345,22 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         put_x1(z1, ds1);                                                // x2^T is dead: rebuild x1^T, keep silu'(z1)
         // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   
         issue_mma([&]() {
-            tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T1_COL, dW2m, WLO, dZm, ALO, id_mm64, false);
+            tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + t1col, dW2m, WLO, dZm, ALO, id_mm64, false);
             tc::mma_commit(bar_mma);
             tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW2_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
-            tc::mma_commit(bar_wg);              // waited for at the top of the next tile (before x1^T is rebuilt)
+            tc::mma_commit(bar_wg);              // waited for before x1^T is rewritten (below, or after the last tile)
         }, false);
         first_tile = false;
         if (next < tiles) load_z1(tn, z1);                              // next tile's gather, behind the MMAs
         wait_mma();
+        if (next < tiles) {                  // next tile's x1^T and its first MMA, which then runs under the epilogue
+            wait_wgrad();
+            put_x1(z1, nullptr);
+            issue_g1(T1B_COL - t1col);
+        }
         {
             float v[16];
-            tc::tmem_ld16(lane_base + T1_COL + ec, v);
+            tc::tmem_ld16(lane_base + t1col + ec, v);
             // dz1 = dx1 * silu'(z1): stored per edge (for the column-grouped sum dS) and reduced over each row's
             // edges into per-run partials (dP, see segment.cu) by a thread-local running sum
             int rid = ((e0 + ec) >> 4) + ti.mis[ec];
@@ -368,7 +390,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int c = 0; c < 3; ++c) dd_out[(int64_t)(e0 + tid) * 3 + c] = fmaf(dr2, ti.d[tid][c], ti.ddir[tid][c]);
         }
-        cur ^= 1;
+        cur = cur == 2 ? 0 : cur + 1;
+        t1col = T1B_COL - t1col;
     }
     // ---- per-CTA partials: weight gradients from TMEM, vector gradients combined over the 4 edge groups
     if (!first_tile) wait_wgrad();
