@@ -309,13 +309,29 @@ def main():
         dom = max(fam, key=lambda k: fam[k][0])
         flops = {'edge_fwd': edge_flops(E, nf, False), 'edge_bwd': 2 * edge_flops(E, nf, False)}
         roof = None
-        if dom in flops and avg[dom] > 0:
+        if dom not in flops:
+            # the radius-graph / small-batch configs are dominated by K0 (neighbour list): integer + fp64 work whose
+            # algorithmic traffic is the positions in and the edge list out
+            k0_bytes = n_atoms * 24 + E * 8 + (n_atoms + 1) * 4
+            modelled = {'edges': k0_bytes}
+            cand = dom if dom in modelled else max(flops, key=lambda k: fam[k][0])
+            if cand in modelled and avg[cand] > 0:
+                a = modelled[cand] / (avg[cand] * 1e-3) / 1e9
+                roof = {'kernel': 'K0 neighbour list (k_edges_survivors + k_edges_hits x2 + scans)', 'bound': 'hbm',
+                        'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': a / pk['hbm_gbs'], 'traffic': None,
+                        'peak_source': pk['source'] + ' HBM copy bandwidth',
+                        'algorithmic_bytes_per_launch': modelled[cand],
+                        'note': 'dominant kernel family of this config; latency-bound fp64 image tests over 27 n points per '
+                                'molecule, far from the HBM roofline by construction (DESIGN.md section 4)'}
+            else:
+                dom = cand
+        if roof is None and dom in flops and avg[dom] > 0:
             ach = flops[dom] / (avg[dom] * 1e-3) / 1e12
             tc_mode = args.precision != 'fp32'
             kname = 'k_' + dom + ('_tc' if tc_mode else '')
             # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
-            # (profiles/r1_edge_bwd_tc_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
-            traffic = {'k_edge_bwd_tc': 496.9e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
+            # (profiles/r1b_tc_kernels_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
+            traffic = {'k_edge_bwd_tc': 497.6e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
             mma_per_gemm = {'fp32': 0, 'fp32_tc': 3, 'bf16': 1}[args.precision]
             roof = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'],
                     'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
