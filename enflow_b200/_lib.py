@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libenflow_b200.so')
 _lib = None
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+f64, u64, box3 = C.c_double, C.c_uint64, C.POINTER(C.c_double)
 
 
 class Dims(C.Structure):
@@ -32,6 +33,11 @@ SIGNATURES = {
     'enflow_timing_read': (i32, [C.POINTER(f32), C.POINTER(i32)]),
     'enflow_adam_step': (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]),
     'enflow_param_layout': (i64, [i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+    'enflow_lj_prior_workspace_doubles': (i64, [i32]),
+    'enflow_lj_prior_forces': (i32, [vp, i32, box3, f64, f64, vp, vp, vp, vp]),
+    'enflow_lj_prior_minimize': (i32, [vp, i32, box3, f64, f64, i32, f64, f64, vp, vp]),
+    'enflow_lj_prior_velocities': (i32, [vp, i32, f64, u64, vp]),
+    'enflow_lj_prior_run': (i32, [vp, vp, i32, box3, f64, f64, f64, f64, f64, i32, u64, u64, vp, vp, vp]),
     'enflow_edges_workspace_ints': (i64, [i32]),
     'enflow_build_edges': (i32, [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     'enflow_build_col_perm': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),

@@ -105,6 +105,29 @@ int enflow_adam_step(float* params, const float* grads, float* exp_avg, float* e
     return enf_adam_step(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, ST(stream));
 }
 
+int64_t enflow_lj_prior_workspace_doubles(int N) { return enf_lj_prior_workspace_doubles(N); }
+int enflow_lj_prior_forces(const double* pos, int N, const double* box, double softening, double cutoff, double* ws,
+                           double* force, double* energy, void* stream) {
+    ENF_CHECK_ARG(N >= 0 && box && box[0] > 0 && box[1] > 0 && box[2] > 0 && cutoff > 0, "lj_prior: bad box/cutoff");
+    return enf_lj_prior_forces(pos, N, box, softening, cutoff, ws, force, energy, ST(stream));
+}
+int enflow_lj_prior_minimize(double* pos, int N, const double* box, double softening, double cutoff, int iters,
+                             double rate, double cap, double* ws, void* stream) {
+    ENF_CHECK_ARG(N >= 0 && box && box[0] > 0 && box[1] > 0 && box[2] > 0 && cutoff > 0, "lj_prior: bad box/cutoff");
+    return enf_lj_prior_minimize(pos, N, box, softening, cutoff, iters, rate, cap, ws, ST(stream));
+}
+int enflow_lj_prior_velocities(double* vel, int N, double kBT, uint64_t seed, void* stream) {
+    ENF_CHECK_ARG(N >= 0 && kBT >= 0, "lj_prior: negative size or temperature");
+    return enf_lj_prior_velocities(vel, N, kBT, seed, ST(stream));
+}
+int enflow_lj_prior_run(double* pos, double* vel, int N, const double* box, double softening, double cutoff, double dt,
+                        double a, double kBT, int n_steps, uint64_t seed, uint64_t step0, double* ws, double* energy,
+                        void* stream) {
+    ENF_CHECK_ARG(N >= 0 && box && box[0] > 0 && box[1] > 0 && box[2] > 0 && cutoff > 0, "lj_prior: bad box/cutoff");
+    ENF_CHECK_ARG(a >= 0 && a <= 1 && kBT >= 0 && n_steps >= 0, "lj_prior: a=%g outside [0,1] or negative kBT/steps", a);
+    return enf_lj_prior_run(pos, vel, N, box, softening, cutoff, dt, a, kBT, n_steps, seed, step0, ws, energy, ST(stream));
+}
+
 int64_t enflow_edges_workspace_ints(int N) { return enf_edges_workspace_ints(N); }
 
 int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const float* r_cut, const int* mol_off,

@@ -63,6 +63,17 @@ int enf_nll_bwd(const float* pos, const float* vel, const float* h, const float*
                 float* dg, float* dldj, cudaStream_t st);
 int enf_ldj_total(const float* ldj_mol, int B, const float* log_q, float* ldj, cudaStream_t st);
 
+// prior sampler for generate (lj_prior.cu): periodic soft-LJ forces + LangevinMiddle steps, fp64, host box[3]
+int64_t enf_lj_prior_workspace_doubles(int N);
+int enf_lj_prior_forces(const double* pos, int N, const double* box, double soft, double rc, double* ws, double* force,
+                        double* energy, cudaStream_t st);
+int enf_lj_prior_minimize(double* pos, int N, const double* box, double soft, double rc, int iters, double rate,
+                          double cap, double* ws, cudaStream_t st);
+int enf_lj_prior_velocities(double* vel, int N, double kBT, uint64_t seed, cudaStream_t st);
+int enf_lj_prior_run(double* pos, double* vel, int N, const double* box, double soft, double rc, double dt, double a,
+                     double kBT, int n_steps, uint64_t seed, uint64_t step0, double* ws, double* energy,
+                     cudaStream_t st);
+
 // tensor-core (tcgen05) edge kernels; mode 1 = bf16x3 split (fp32-accurate), mode 2 = bf16
 int64_t enf_tc_pack_bytes();
 int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t st);

@@ -66,6 +66,9 @@ class Main:
         dtype = args[label]['type']
         cls = getattr(importlib.import_module(f'enflow_b200.data.{dtype}'), f'{dtype.upper()}Dataset')
         kwargs = {k: v for k, v in args[label].items() if k not in ('batch_size', 'type')}
+        if 'units' in args:                                         # main.py:71-72
+            kwargs.setdefault('dist_unit', args['units'].get('dist', 'ang'))
+            kwargs.setdefault('time_unit', args['units'].get('time', 'pico'))
         return cls(**kwargs)
 
     def setup(self, input):
@@ -94,6 +97,11 @@ class Main:
             softening = float(args['training']['loss']['softening'])
         if self.mode == 'gen':
             batch_size = int(args['dataset'].get('batch_size', 1))
+            if checkpoint and args['dataset']['type'] == 'lj':      # main.py:118-123: the prior is the trained model's
+                ds = args['dataset']
+                ds['node_nf'], ds['softening'], ds['temp'] = node_nf, softening, lj_to_kelvin(lj_kBT)
+                ds['box'] = [float(b) for b in ds['box']]
+                ds['n_atoms'] = int(ds['n_atoms'])
         else:
             tr = args.get('training', {})
             batch_size = int(tr['batch_size'] if 'batch_size' in tr else args['dataset']['batch_size'])

@@ -143,6 +143,23 @@ int enflow_nll_bwd(const float* pos, const float* vel, const float* h, const flo
                    int nf, int max_n, float kBT, float softening, const float* dloss, float* dpos, float* dvel,
                    float* dh, float* dg, float* dldj, void* stream);
 
+/* ---- prior sampler for generate: the soft Lennard-Jones Langevin run that the reference does through
+ * OpenMM (enflow/data/lj.py:32-89 potential and cutoff, enflow/data/simulated.py:109-132 LangevinMiddleIntegrator,
+ * minimisation, Maxwell velocities), in the reduced units of the likelihood (sigma = eps = mass = 1).
+ * pos, vel, force: device fp64 [N,3]; box: HOST double[3] (periodic cell); ws: enflow_lj_prior_workspace_doubles(N)
+ * device doubles; energy: device double[2] = {potential, kinetic} or NULL.
+ * run: n_steps of  v += dt f; x += dt/2 v; v = a v + sqrt(kBT (1 - a^2)) N(0,1); x += dt/2 v  with a = exp(-friction dt);
+ * noise = Philox4x32-10(seed; step0 + s, atom): the same (seed, step0) reproduces the trajectory bit for bit. */
+int64_t enflow_lj_prior_workspace_doubles(int N);
+int enflow_lj_prior_forces(const double* pos, int N, const double* box, double softening, double cutoff, double* ws,
+                           double* force, double* energy, void* stream);
+int enflow_lj_prior_minimize(double* pos, int N, const double* box, double softening, double cutoff, int iters,
+                             double rate, double cap, double* ws, void* stream);
+int enflow_lj_prior_velocities(double* vel, int N, double kBT, uint64_t seed, void* stream);
+int enflow_lj_prior_run(double* pos, double* vel, int N, const double* box, double softening, double cutoff, double dt,
+                        double a, double kBT, int n_steps, uint64_t seed, uint64_t step0, double* ws, double* energy,
+                        void* stream);
+
 /* ---- whole flow: LFIntegrator.forward / its backward / .reverse (enflow/flow/dynamics.py:10-37) --
  * One call enqueues every kernel of the pass on `stream`; no host synchronisation inside.
  * workspace: enflow_flow_workspace_bytes(dims, training) bytes, reused by the matching backward.

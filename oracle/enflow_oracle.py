@@ -252,3 +252,35 @@ def train_step(sd, L, batch, dt, eps, kBT, softening):
     loss.backward()
     grads = {k: v.grad for k, v in p.items()}
     return loss.detach(), grads, {k: v.detach() for k, v in state.items()}, ldj.detach(), ldj_mol.detach()
+
+
+# ---- prior sampler for generate -----------------------------------------------------------------
+# PARITY UNPINNED: the reference runs this through OpenMM (CustomNonbondedForce + LangevinMiddleIntegrator), which
+# is not installed here and has no golden vectors in the reference.  These restate the PUBLISHED definitions the
+# reference configures (enflow/data/lj.py:65 energy expression, :74-75 CutoffPeriodic at cutoff*sigma, no switching;
+# OpenMM LangevinMiddleIntegrator: v += dt f/m; x += dt/2 v; v = a v + sqrt(kT(1-a^2)/m) R; x += dt/2 v,
+# a = exp(-friction dt)) in reduced units (sigma = eps = m = 1) and serve as the checker of lj_prior.cu.
+def lj_prior_energy_forces(pos, box, softening, cutoff):
+    """numpy fp64: total energy and forces [N,3] of the periodic soft-LJ fluid (minimum image, plain cutoff)."""
+    import numpy as np
+    pos = np.asarray(pos, dtype=np.float64)
+    box = np.asarray(box, dtype=np.float64)
+    d = pos[:, None, :] - pos[None, :, :]
+    d -= box * np.rint(d / box)
+    r = np.sqrt((d ** 2).sum(-1))
+    mask = (r < cutoff) & ~np.eye(len(pos), dtype=bool)
+    q = np.where(mask, 1.0 / (softening + np.where(mask, r, 1.0)), 0.0)
+    u_pair = 4.0 * (q ** 12 - q ** 6)
+    g = np.where(mask, 4.0 * (12.0 * q ** 13 - 6.0 * q ** 7) / np.where(mask, r, 1.0), 0.0)       # -dU/dr / r
+    return 0.5 * u_pair.sum(), (g[:, :, None] * d).sum(1)
+
+
+def langevin_middle_step(pos, vel, box, softening, cutoff, dt, a, kBT, noise):
+    """One LangevinMiddle step with the given standard-normal noise [N,3] (numpy fp64)."""
+    import numpy as np
+    _, f = lj_prior_energy_forces(pos, box, softening, cutoff)
+    v = vel + dt * f
+    x = pos + 0.5 * dt * v
+    v = a * v + np.sqrt(kBT * (1.0 - a * a)) * noise
+    x = x + 0.5 * dt * v
+    return x, v

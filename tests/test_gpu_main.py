@@ -42,3 +42,8 @@ def test_train_checkpoint_resume_generate(tmp_path):
     assert ok, 'forward(reverse(x)) must reproduce x (main.py:275-278)'
     assert os.path.exists(tmp_path / 'h.out') and os.path.exists(tmp_path / 'test_out.xyz')
     assert out.neg_ldj_mol.shape[0] == 64
+    # generate from the reference's own prior: soft-LJ Langevin frames sampled on the GPU
+    gen_lj = _cfg(tmp_path, 'generate_lj.yaml', dataset__n_iter=600, dataset__n_atoms=64, dataset__box=[16.0, 16.0, 16.0])
+    out, ok = Main()(gen_lj)
+    assert ok and out.pos.shape == (64, 3) and torch.isfinite(out.pos).all()
+    assert os.path.exists(tmp_path / 'lj_log.txt') and os.path.exists(tmp_path / 'lj_traj.xyz')
