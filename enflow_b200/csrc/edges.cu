@@ -345,6 +345,11 @@ template <typename T>
 int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int* mol_off, int B, int N, int E_cap,
                       int* row, int* col, int* rowptr, int* ref_pos, int* E_dev, int* status, int* ws,
                       cudaStream_t st) {
+    if (B == 0 || N == 0) {          // empty batch: an empty, well-formed list
+        cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)N + 1), st);
+        cudaMemsetAsync(E_dev, 0, sizeof(int) * 2, st);
+        return ENF_OK;
+    }
     const int64_t n27 = 27LL * N;
     int* qrank = ws;
     int* idmap = qrank + n27;

@@ -176,6 +176,10 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
     ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
     const int nf = d.nf;
     const size_t N = d.N;
+    if (d.B == 0 || d.N == 0) {          // empty batch: nothing to transform, log-det 0
+        cudaMemsetAsync(ldj, 0, sizeof(float), st);
+        return ENF_OK;
+    }
     cudaMemsetAsync(ldj_mol, 0, sizeof(float) * d.B, st);
     for (int l = 0; l < d.L; ++l) {
         ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
@@ -219,6 +223,7 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
     Workspace w = carve(d, workspace, 1);
     ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
     const int nf = d.nf;
+    if (d.B == 0 || d.N == 0) return ENF_OK;
     for (int l = d.L - 1; l >= 0; --l) {
         const LayerSave& sv = w.layer[l];
         const float* lp = layer_params(params, nf, l);
@@ -277,6 +282,7 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
     Workspace w = carve(d, workspace, 0);
     ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
     const int nf = d.nf;
+    if (d.B == 0 || d.N == 0) return ENF_OK;
     if (neg_ldj_mol) cudaMemsetAsync(neg_ldj_mol, 0, sizeof(float) * d.B, st);
     for (int l = 0; l < d.L; ++l) {
         ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));

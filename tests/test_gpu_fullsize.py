@@ -1,0 +1,82 @@
+"""BASELINE.json's full-size configuration (C2: 1024 molecules x 29 atoms, 5 layers, hidden 128) on the default
+fp32-accurate tensor-core path, through size-independent properties: the oracle needs minutes per step at this size,
+so parity is anchored on (1) a seeded sub-batch checked against the oracle, (2) molecules being independent --
+every per-molecule result of the big batch must equal the same molecule processed in a small batch, (3) the exact
+inverse, (4) bitwise determinism of loss and gradients."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import gpu_batch, rel_err, to_np
+from oracle import enflow_oracle as orc
+
+pytestmark = pytest.mark.gpu
+B, NF, L = 1024, 5, 5
+
+
+def _model(precision='fp32_tc'):
+    from enflow_b200.data import synthetic as syn
+    from gpu_util import build_model
+    return build_model(syn.make_weights(NF, 128, L, seed=0), NF, L, precision=precision)
+
+
+def _take(arrs, lo, hi):
+    off = np.concatenate([[0], np.cumsum(arrs['N'])])
+    sl = slice(off[lo], off[hi])
+    out = {k: arrs[k][sl] for k in ('h', 'g', 'pos', 'vel', 'box')}
+    out['N'], out['r_cut'] = arrs['N'][lo:hi], arrs['r_cut'][lo:hi]
+    return out, sl
+
+
+def test_full_size_c2_properties():
+    from enflow_b200.data import synthetic as syn
+    from enflow_b200.flow.loss import Alchemical_NLL
+    arrs = syn.make_batch('c2', B, ragged=True)
+    n_atoms = int(arrs['N'].sum())
+    eps = syn.make_noise(n_atoms, NF)
+    model = _model()
+    nll = Alchemical_NLL(kBT=syn.TRAIN_KBT, softening=syn.TRAIN_SOFTENING)
+    runs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        out, ldj = model(gpu_batch(arrs), eps=torch.as_tensor(eps))
+        loss = nll(out, ldj)
+        loss.backward()
+        runs.append((loss.detach().clone(), out.pos.detach().clone(), out.g.detach().clone(), out.ldj_mol.detach().clone(),
+                     model.flat_grads.clone()))
+    # (4) determinism at full size
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b)
+    assert torch.isfinite(runs[0][4]).all() and float(runs[0][4].abs().max()) > 0
+    # (2) independence: molecules 100..116 alone give the same latents and per-molecule log-det
+    sub, sl = _take(arrs, 100, 116)
+    with torch.no_grad():
+        o2, _ = model(gpu_batch(sub), eps=torch.as_tensor(eps[sl]))
+    assert rel_err(to_np(o2.pos), to_np(runs[0][1][sl])) < 2e-6
+    assert rel_err(to_np(o2.g), to_np(runs[0][2][sl])) < 2e-6
+    assert rel_err(to_np(o2.ldj_mol), to_np(runs[0][3][100:116])) < 2e-6
+    # (1) the same sub-batch against the oracle (fp64 restatement of the reference)
+    p = orc.params_to_torch({k: v for k, v in syn.make_weights(NF, 128, L, seed=0).items()})
+    ref, _, ref_ldj_mol = orc.lf_forward(p, L, orc.to_torch(sub), syn.TRAIN_DT, torch.as_tensor(eps[sl], dtype=torch.float64))
+    for k in ('pos', 'vel', 'h', 'g'):
+        assert rel_err(to_np(getattr(o2, k)), ref[k].numpy()) < 1e-5, k
+    assert rel_err(to_np(o2.ldj_mol), ref_ldj_mol.numpy()) < 1e-5
+    # (3) exact inverse at full size
+    with torch.no_grad():
+        out, _ = model(gpu_batch(arrs), eps=torch.as_tensor(eps))
+        fwd_ldj = out.ldj_mol.clone()
+        back = model.reverse(out, quantize=True)
+    assert rel_err(to_np(back.pos), arrs['pos']) < 1e-5
+    assert rel_err(to_np(back.vel), arrs['vel']) < 1e-5
+    assert np.array_equal(to_np(back.h), arrs['h'])
+    assert rel_err(to_np(back.neg_ldj_mol), -to_np(fwd_ldj)) < 1e-5
+
+
+def test_empty_batch_is_a_no_op():
+    arrs = {'h': np.zeros((0, NF)), 'g': np.zeros((0, NF)), 'pos': np.zeros((0, 3)), 'vel': np.zeros((0, 3)),
+            'box': np.zeros((0, 3)), 'N': np.zeros(0, dtype=np.int64), 'r_cut': np.zeros(0, dtype=np.float32)}
+    model = _model()
+    with torch.no_grad():
+        out, ldj = model(gpu_batch(arrs), eps=torch.zeros(0, NF))
+    assert out.pos.shape == (0, 3) and out.h.shape == (0, NF)
+    assert float(ldj) == 0.0
