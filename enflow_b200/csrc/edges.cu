@@ -13,6 +13,8 @@
 
 namespace {
 
+constexpr int ACT_SHIFT = 24;       // active entry = image index << 24 | atom (molecules of < 16.7 M atoms)
+
 template <typename T>
 __device__ __forceinline__ double ld3(const T* p, int i, int c) { return (double)p[(int64_t)i * 3 + c]; }
 
@@ -78,9 +80,9 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
     for (int start = 0; start < total; start += 256) {
         const int ip = start + threadIdx.x;
         bool keep = false, act = false;
-        int a = 0;
+        int a = 0, k = 0;
         if (ip < total) {
-            const int k = ip / n;
+            k = ip / n;
             a = ip - k * n;
             const double px = __dadd_rn(ld3(pos, o + a, 0), shift_of(k % 3, bx));
             const double py = __dadd_rn(ld3(pos, o + a, 1), shift_of((k / 3) % 3, by));
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
         if (ip < total) {
             qrank[base + ip] = keep ? rank : -1;
             if (keep) idmap[base + rank] = a;
-            if (act) active[base + pre_a + __popc(bal_a & lt)] = ip;
+            if (act) active[base + pre_a + __popc(bal_a & lt)] = (k << ACT_SHIFT) | a;      // (image, atom): no division later
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -125,8 +127,9 @@ __global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, c
                                                      const int* __restrict__ idmap, const int* __restrict__ nsurv,
                                                      const int* __restrict__ active, const int* __restrict__ nactive,
                                                      int* __restrict__ cnt_csr, int* __restrict__ cnt_ref,
-                                                     int* __restrict__ row, int* __restrict__ col,
-                                                     int* __restrict__ ref_pos, int E_cap, int* __restrict__ status) {
+                                                     unsigned* __restrict__ hmask, int* __restrict__ row,
+                                                     int* __restrict__ col, int* __restrict__ ref_pos, int E_cap,
+                                                     int* __restrict__ status) {
     const int m = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int o = mol_off[m], n = mol_off[m + 1] - o;
@@ -135,22 +138,29 @@ __global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, c
     const float rcf = r_cut[m];
     const double r_sq = (double)__fmul_rn(rcf, rcf);          // base.py:133, fp32 product (Q9)
     const int ns = nsurv[m], na = nactive[m];
+    // molecules of up to 64 atoms: the counting pass leaves its hit ballots behind (two words per active point)
+    // and the fill pass replays them instead of repeating the fp64 distance tests
+    const bool masked = n <= 64;
     for (int t = wid + 8 * blockIdx.y; t < na; t += 8 * gridDim.y) {     // gridDim.y CTAs share a large molecule
-        const int ipl = active[base + t];
-        const int k = ipl / n, a = ipl - k * n;
+        const int ent = active[base + t];
+        const int k = ent >> ACT_SHIFT, a = ent & ((1 << ACT_SHIFT) - 1);
         const int i = o + a;
-        const int64_t gw = 27LL * i + k, ip = base + ipl;
-        const double px = __dadd_rn(ld3(pos, i, 0), shift_of(k % 3, bx));
-        const double py = __dadd_rn(ld3(pos, i, 1), shift_of((k / 3) % 3, by));
-        const double pz = __dadd_rn(ld3(pos, i, 2), shift_of(k / 9, bz));
+        const int64_t gw = 27LL * i + k, ip = base + (int64_t)k * n + a;
+        const int kx = k % 3, ky = (k / 3) % 3, kz = k / 9;
+        const double px = __dadd_rn(ld3(pos, i, 0), shift_of(kx, bx));
+        const double py = __dadd_rn(ld3(pos, i, 1), shift_of(ky, by));
+        const double pz = __dadd_rn(ld3(pos, i, 2), shift_of(kz, bz));
         int running = 0;
         int out_csr = 0, out_ref = 0;
-        if (FILL) { out_csr = cnt_csr[gw]; out_ref = cnt_ref[ip]; }
+        if (FILL) { out_csr = cnt_csr[gw]; out_ref = cnt_ref ? cnt_ref[ip] : 0; }
         for (int j0 = 0; j0 < n; j0 += 32) {
             const int j = j0 + lane;
             bool hit = false;
             int lab = 0;
-            if (j < n) {
+            if (FILL && masked) {
+                hit = (hmask[(base + t) * 2 + (j0 >> 5)] >> lane) & 1u;
+                if (hit) lab = j < ns ? idmap[base + j] : j;
+            } else if (j < n) {
                 const double dx = __dsub_rn(px, ld3(pos, o + j, 0));
                 const double dy = __dsub_rn(py, ld3(pos, o + j, 1));
                 const double dz = __dsub_rn(pz, ld3(pos, o + j, 2));
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, c
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (!FILL && masked && lane == 0) hmask[(base + t) * 2 + (j0 >> 5)] = bal;
             if (FILL && hit) {
                 const int r = running + __popc(bal & ((1u << lane) - 1u));
                 const int e = out_csr + r;
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, c
             }
             running += __popc(bal);
         }
-        if (!FILL && lane == 0) { cnt_csr[gw] = running; cnt_ref[ip] = running; }
+        if (!FILL && lane == 0) { cnt_csr[gw] = running; if (cnt_ref) cnt_ref[ip] = running; }
     }
 }
 
@@ -338,7 +349,8 @@ int64_t enf_edges_workspace_ints(int N) {
     const int64_t n27 = 27LL * N;
     const int64_t nb = (n27 + SCAN_CHUNK - 1) / SCAN_CHUNK;
     // qrank, idmap, cnt_csr(+1), cnt_ref(+1), nsurv(<=N), atom_mol(N), colcnt(N+1), cursor(N), scan sums
-    return 4 * n27 + 2 + 4LL * N + 1 + 2 * nb + 64 + n27 + N + 4;
+    // ... active (27N), nactive (N), hit ballots (2 x 27N)
+    return 4 * n27 + 2 + 4LL * N + 1 + 2 * nb + 64 + n27 + N + 4 + 2 * n27;
 }
 
 template <typename T>
@@ -361,18 +373,20 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     const int64_t nb_scan = (n27 + SCAN_CHUNK - 1) / SCAN_CHUNK;
     int* active = sums + 2 * nb_scan + 64;    // 27N
     int* nactive = active + n27;              // B <= N
-    cudaMemsetAsync(cnt_csr, 0, sizeof(int) * (2 * n27 + 2), st);
+    unsigned* hmask = reinterpret_cast<unsigned*>(nactive + N);      // 2 x 27N
+    if (!ref_pos) cnt_ref = nullptr;          // reference order not requested: one array to count, zero and scan
+    cudaMemsetAsync(cnt_csr, 0, sizeof(int) * ((cnt_ref ? 2 : 1) * n27 + (cnt_ref ? 2 : 1)), st);
     enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv, active, nactive);
     // large molecules: several CTAs per molecule (the active list of a 500-atom fragment has ~3000 entries)
     int ysplit = (B > 0 ? N / B : 1) / 24;
     ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
     const dim3 hgrid(B, ysplit);
     enf_count_launch(), k_edges_hits<T, false><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
-                                                                  cnt_csr, cnt_ref, nullptr, nullptr, nullptr, E_cap, status);
+                                                                  cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
     enf_count_launch(), k_edges_hits<T, true><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
-                                                                 cnt_csr, cnt_ref, row, col, ref_pos, E_cap, status);
+                                                                 cnt_csr, cnt_ref, hmask, row, col, ref_pos, E_cap, status);
     enf_count_launch(), k_rowptr<<<(N + 255) / 256, 256, 0, st>>>(cnt_csr, N, rowptr);
     enf_count_launch(), k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
     ENF_CHECK_LAUNCH();
