@@ -118,10 +118,98 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
     if (threadIdx.x == 0) { nsurv[m] = running_s; nactive[m] = running_a; }
 }
 
+// One CTA per molecule, one THREAD per active image point, looping over the molecule's atoms (positions converted
+// to fp64 once and staged in shared memory together with id_mapping when the molecule has at most HIT_SM atoms;
+// every lane reads the same atom: a broadcast).  FILL=false counts hits, FILL=true writes them in atom order, so a
+// row's edges come out in the same (image, atom) order as before.  Molecules of up to 64 atoms: the counting pass
+// leaves a 64-bit hit mask per point behind and the fill pass replays it instead of repeating the fp64 tests.
+// cnt_csr / cnt_ref are zero-initialised by the caller; only active entries are touched.
+constexpr int HIT_SM = 512, HIT_T = 128;
+
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(HIT_T) k_edges_hits(const T* __restrict__ pos, const T* __restrict__ box,
+                                                       const float* __restrict__ r_cut,
+                                                       const int* __restrict__ mol_off, const int* __restrict__ qrank,
+                                                       const int* __restrict__ idmap, const int* __restrict__ nsurv,
+                                                       const int* __restrict__ active, const int* __restrict__ nactive,
+                                                       int* __restrict__ cnt_csr, int* __restrict__ cnt_ref,
+                                                       unsigned* __restrict__ hmask, int* __restrict__ row,
+                                                       int* __restrict__ col, int* __restrict__ ref_pos, int E_cap,
+                                                       int* __restrict__ status) {
+    __shared__ double spx[HIT_SM], spy[HIT_SM], spz[HIT_SM];
+    __shared__ int sid[HIT_SM];
+    const int m = blockIdx.x;
+    const int o = mol_off[m], n = mol_off[m + 1] - o;
+    const int64_t base = 27LL * o;
+    const double bx = ld3(box, o, 0), by = ld3(box, o, 1), bz = ld3(box, o, 2);
+    const float rcf = r_cut[m];
+    const double r_sq = (double)__fmul_rn(rcf, rcf);          // base.py:133, fp32 product (Q9)
+    const int ns = nsurv[m], na = nactive[m];
+    const bool staged = n <= HIT_SM, masked = n <= 64;
+    if (staged) {
+        for (int a = threadIdx.x; a < n; a += HIT_T) {
+            spx[a] = ld3(pos, o + a, 0); spy[a] = ld3(pos, o + a, 1); spz[a] = ld3(pos, o + a, 2);
+            sid[a] = a < ns ? idmap[base + a] : a;
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x + HIT_T * blockIdx.y; t < na; t += HIT_T * gridDim.y) {   // gridDim.y CTAs share a large molecule
+        const int ent = active[base + t];
+        const int k = ent >> ACT_SHIFT, a = ent & ((1 << ACT_SHIFT) - 1);
+        const int i = o + a;
+        const int64_t gw = 27LL * i + k, ip = base + (int64_t)k * n + a;
+        const double px = __dadd_rn(staged ? spx[a] : ld3(pos, i, 0), shift_of(k % 3, bx));
+        const double py = __dadd_rn(staged ? spy[a] : ld3(pos, i, 1), shift_of((k / 3) % 3, by));
+        const double pz = __dadd_rn(staged ? spz[a] : ld3(pos, i, 2), shift_of(k / 9, bz));
+        int e = 0, rr = 0;
+        if (FILL) { e = cnt_csr[gw]; rr = cnt_ref ? cnt_ref[ip] : 0; }
+        if (FILL && masked) {
+            unsigned w0 = hmask[(base + t) * 2], w1 = hmask[(base + t) * 2 + 1];
+            while (w0 | w1) {
+                int j;
+                if (w0) { j = __ffs(w0) - 1; w0 &= w0 - 1; }
+                else { j = 32 + __ffs(w1) - 1; w1 &= w1 - 1; }
+                if (e < E_cap) { row[e] = i; col[e] = o + sid[j]; if (ref_pos) ref_pos[e] = rr; }
+                ++e; ++rr;
+            }
+            continue;
+        }
+        int cnt = 0;
+        unsigned w0 = 0, w1 = 0;
+        for (int j = 0; j < n; ++j) {
+            const double dx = __dsub_rn(px, staged ? spx[j] : ld3(pos, o + j, 0));
+            const double dy = __dsub_rn(py, staged ? spy[j] : ld3(pos, o + j, 1));
+            const double dz = __dsub_rn(pz, staged ? spz[j] : ld3(pos, o + j, 2));
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 < r_sq) {
+                // base.py:137: the atom column is ALSO indexed through id_mapping (Q6)
+                int lab;
+                if (j < ns) lab = staged ? sid[j] : idmap[base + j];
+                else { lab = j; atomicOr(status, 2); }            // the reference would raise IndexError here
+                if (lab != a) {                                     // base.py:139 (Q11)
+                    if (FILL) {
+                        if (e < E_cap) { row[e] = i; col[e] = o + lab; if (ref_pos) ref_pos[e] = rr; }
+                        ++e; ++rr;
+                    } else {
+                        ++cnt;
+                        if (j < 32) w0 |= 1u << j;
+                        else if (j < 64) w1 |= 1u << (j - 32);
+                    }
+                }
+            }
+        }
+        if (!FILL) {
+            cnt_csr[gw] = cnt;
+            if (cnt_ref) cnt_ref[ip] = cnt;
+            if (masked) { hmask[(base + t) * 2] = w0; hmask[(base + t) * 2 + 1] = w1; }
+        }
+    }
+}
+
 // One CTA per molecule, one warp per active image point. FILL=false counts hits, FILL=true writes them.
 // cnt_csr / cnt_ref are zero-initialised by the caller; only active entries are touched.
 template <typename T, bool FILL>
-__global__ void __launch_bounds__(256) k_edges_hits(const T* __restrict__ pos, const T* __restrict__ box,
+__global__ void __launch_bounds__(256) k_edges_hits_warp(const T* __restrict__ pos, const T* __restrict__ box,
                                                      const float* __restrict__ r_cut,
                                                      const int* __restrict__ mol_off, const int* __restrict__ qrank,
                                                      const int* __restrict__ idmap, const int* __restrict__ nsurv,
@@ -381,12 +469,22 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     int ysplit = (B > 0 ? N / B : 1) / 24;
     ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
     const dim3 hgrid(B, ysplit);
-    enf_count_launch(), k_edges_hits<T, false><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
-                                                                  cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);
+    // small molecules: one thread per active point; large ones (long atom loops, few points per SM): one warp per point
+    const bool per_thread = N <= 96LL * B;
+    if (per_thread)
+        enf_count_launch(), k_edges_hits<T, false><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+                                                                        cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);
+    else
+        enf_count_launch(), k_edges_hits_warp<T, false><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+                                                                           cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
-    enf_count_launch(), k_edges_hits<T, true><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
-                                                                 cnt_csr, cnt_ref, hmask, row, col, ref_pos, E_cap, status);
+    if (per_thread)
+        enf_count_launch(), k_edges_hits<T, true><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+                                                                       cnt_csr, cnt_ref, hmask, row, col, ref_pos, E_cap, status);
+    else
+        enf_count_launch(), k_edges_hits_warp<T, true><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+                                                                          cnt_csr, cnt_ref, hmask, row, col, ref_pos, E_cap, status);
     enf_count_launch(), k_rowptr<<<(N + 255) / 256, 256, 0, st>>>(cnt_csr, N, rowptr);
     enf_count_launch(), k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
     ENF_CHECK_LAUNCH();
