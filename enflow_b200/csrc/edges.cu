@@ -400,6 +400,63 @@ __global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, c
     }
 }
 
+// Large molecules: one warp per group of 32 consecutive columns (lane <-> column) scans the edges of the molecules
+// those columns belong to once (coalesced, eight loads in flight) and appends every match to its column's list in
+// edge order: lanes holding the same column are ranked with match.any, the per-column write positions live in
+// shared memory.  Stable, no serial chunk loop, no atomics.
+__global__ void __launch_bounds__(256) k_col_fill_warp(const int* __restrict__ col, const int* __restrict__ rowptr,
+                                                        const int* __restrict__ mol_off, int B, int N,
+                                                        const int* __restrict__ colptr, int* __restrict__ perm,
+                                                        int E_cap, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    __shared__ int pos_s[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * 8 + wid;
+    const int c0 = 32 * g;
+    if (c0 >= N) return;
+    int* pos = pos_s[wid];
+    pos[lane] = c0 + lane < N ? colptr[c0 + lane] : 0;
+    // edge range: from the molecule of the first column to the molecule of the last one
+    const int cl = lane == 0 ? c0 : min(c0 + 31, N - 1);
+    int lo = 0, hi = B;                                     // mol_off[lo] <= cl < mol_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (mol_off[mid] <= cl) lo = mid; else hi = mid;
+    }
+    const int m_lo = __shfl_sync(0xffffffffu, lo, 0), m_hi = __shfl_sync(0xffffffffu, lo, 31);
+    const int e_lo = rowptr[mol_off[m_lo]];
+    int e_hi = rowptr[mol_off[m_hi + 1]];
+    if (e_hi > E_cap) e_hi = E_cap;
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    for (int e0 = e_lo; e0 < e_hi; e0 += 256) {
+        int cv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + 32 * u + lane;
+            cv[u] = e < e_hi ? col[e] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + 32 * u + lane;
+            const int lc = cv[u] - c0;
+            const bool mine = (unsigned)lc < 32u;
+            const unsigned act = __ballot_sync(0xffffffffu, mine);
+            if (act == 0) continue;
+            unsigned same = 0;
+            int base = 0;
+            if (mine) {
+                same = __match_any_sync(act, lc);
+                base = pos[lc];
+                perm[base + __popc(same & lt)] = e;
+            }
+            __syncwarp();
+            if (mine && (same & lt) == 0) pos[lc] = base + __popc(same);     // one leader per column
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void k_zero_int(int* __restrict__ p, int64_t n, const int* __restrict__ skip) {
     if (skip && *skip) return;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
@@ -510,7 +567,11 @@ int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, in
     enf_count_launch(), k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr, skip);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(colptr, nullptr, N, sums, st, skip));
-    enf_count_launch(), k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap, skip);
+    if (N <= 96LL * B)
+        enf_count_launch(), k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap, skip);
+    else        // large molecules: a CTA per molecule would leave the GPU empty
+        enf_count_launch(), k_col_fill_warp<<<((N + 31) / 32 + 7) / 8, 256, 0, st>>>(col, rowptr, mol_off, B, N, colptr, perm,
+                                                                                     E_cap, skip);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
