@@ -30,7 +30,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ pos, const T* __restrict__ box,
                                                           const float* __restrict__ r_cut,
                                                           const int* __restrict__ mol_off, int B,
-                                                          int* __restrict__ qrank, int* __restrict__ idmap,
+                                                          int* __restrict__ idmap,
                                                           int* __restrict__ nsurv, int* __restrict__ active,
                                                           int* __restrict__ nactive) {
     __shared__ int warp_tot[8], warp_act[8];
@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
         const unsigned lt = (1u << lane) - 1u;
         const int rank = pre + __popc(bal & lt);
         if (ip < total) {
-            qrank[base + ip] = keep ? rank : -1;
             if (keep) idmap[base + rank] = a;
             if (act) active[base + pre_a + __popc(bal_a & lt)] = (k << ACT_SHIFT) | a;      // (image, atom): no division later
         }
@@ -129,7 +128,7 @@ constexpr int HIT_SM = 512, HIT_T = 128;
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(HIT_T) k_edges_hits(const T* __restrict__ pos, const T* __restrict__ box,
                                                        const float* __restrict__ r_cut,
-                                                       const int* __restrict__ mol_off, const int* __restrict__ qrank,
+                                                       const int* __restrict__ mol_off,
                                                        const int* __restrict__ idmap, const int* __restrict__ nsurv,
                                                        const int* __restrict__ active, const int* __restrict__ nactive,
                                                        int* __restrict__ cnt_csr, int* __restrict__ cnt_ref,
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(HIT_T) k_edges_hits(const T* __restrict__ pos,
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) k_edges_hits_warp(const T* __restrict__ pos, const T* __restrict__ box,
                                                      const float* __restrict__ r_cut,
-                                                     const int* __restrict__ mol_off, const int* __restrict__ qrank,
+                                                     const int* __restrict__ mol_off,
                                                      const int* __restrict__ idmap, const int* __restrict__ nsurv,
                                                      const int* __restrict__ active, const int* __restrict__ nactive,
                                                      int* __restrict__ cnt_csr, int* __restrict__ cnt_ref,
@@ -508,8 +507,7 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
         return ENF_OK;
     }
     const int64_t n27 = 27LL * N;
-    int* qrank = ws;
-    int* idmap = qrank + n27;
+    int* idmap = ws + n27;                    // (the first 27N ints of the layout are unused)
     int* cnt_csr = idmap + n27;
     int* cnt_ref = cnt_csr + n27 + 1;
     int* nsurv = cnt_ref + n27 + 1;
@@ -521,7 +519,7 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     unsigned* hmask = reinterpret_cast<unsigned*>(nactive + N);      // 2 x 27N
     if (!ref_pos) cnt_ref = nullptr;          // reference order not requested: one array to count, zero and scan
     cudaMemsetAsync(cnt_csr, 0, sizeof(int) * ((cnt_ref ? 2 : 1) * n27 + (cnt_ref ? 2 : 1)), st);
-    enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, qrank, idmap, nsurv, active, nactive);
+    enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, idmap, nsurv, active, nactive);
     // large molecules: several CTAs per molecule (the active list of a 500-atom fragment has ~3000 entries)
     int ysplit = (B > 0 ? N / B : 1) / 24;
     ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
@@ -529,18 +527,18 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     // small molecules: one thread per active point; large ones (long atom loops, few points per SM): one warp per point
     const bool per_thread = N <= 96LL * B;
     if (per_thread)
-        enf_count_launch(), k_edges_hits<T, false><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+        enf_count_launch(), k_edges_hits<T, false><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, idmap, nsurv, active, nactive,
                                                                         cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);
     else
-        enf_count_launch(), k_edges_hits_warp<T, false><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+        enf_count_launch(), k_edges_hits_warp<T, false><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, idmap, nsurv, active, nactive,
                                                                            cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(cnt_csr, cnt_ref, n27, sums, st));
     if (per_thread)
-        enf_count_launch(), k_edges_hits<T, true><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+        enf_count_launch(), k_edges_hits<T, true><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, idmap, nsurv, active, nactive,
                                                                        cnt_csr, cnt_ref, hmask, row, col, ref_pos, E_cap, status);
     else
-        enf_count_launch(), k_edges_hits_warp<T, true><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, qrank, idmap, nsurv, active, nactive,
+        enf_count_launch(), k_edges_hits_warp<T, true><<<hgrid, 256, 0, st>>>(pos, box, r_cut, mol_off, idmap, nsurv, active, nactive,
                                                                           cnt_csr, cnt_ref, hmask, row, col, ref_pos, E_cap, status);
     enf_count_launch(), k_rowptr<<<(N + 255) / 256, 256, 0, st>>>(cnt_csr, N, rowptr);
     enf_count_launch(), k_edges_finish<<<1, 1, 0, st>>>(cnt_csr, N, E_cap, rowptr, E_dev, status);
