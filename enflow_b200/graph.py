@@ -40,7 +40,7 @@ class GraphedTrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self._step_body()
+                self.warmup_loss = self._step_body().detach().clone()       # real optimizer steps on the example batch
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         model.check_status = False          # no host read-back inside the graph

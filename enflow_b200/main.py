@@ -130,6 +130,8 @@ class Main:
             return
         tr = args['training']
         self.log_interval = int(tr['log_interval'])
+        # not in the reference: replay the whole step as one CUDA graph when the batches share one layout
+        self.cuda_graph = bool(tr.get('cuda_graph', False))
         self.num_epochs = int(tr['num_epochs'])
         # Adam as in main.py:177, as one fused kernel over the flat buffers; its state_dict has torch.optim.Adam's layout
         self.optimizer = FlatAdam(self.model, lr=float(tr['lr']))
@@ -146,6 +148,20 @@ class Main:
             if self.scheduler and 'scheduler_state_dict' in checkpoint:
                 self.scheduler.load_state_dict(checkpoint['scheduler_state_dict'])
 
+    def _graphed_step(self, data):
+        """One optimizer step through `GraphedTrainStep`; None when this batch does not have the captured layout
+        (e.g. the last, shorter batch of an epoch), in which case the caller launches the step eagerly."""
+        from .graph import GraphedTrainStep
+        n_cpu = data.meta()[3]
+        g = getattr(self, '_gstep', None)
+        if g is None:
+            # the capture's warm-up IS this batch's step (one eager step), the capture itself executes nothing
+            self._gstep = GraphedTrainStep(self.model, self.nll, self.optimizer, data, warmup=1)
+            return self._gstep.warmup_loss
+        if not torch.equal(n_cpu, g._n_cpu):
+            return None
+        return g(data)
+
     def train(self):
         if self.world_rank == 0:
             print('Epoch \tTraining Loss \t   Time (s)', flush=True)
@@ -158,14 +174,16 @@ class Main:
             start_time = time.time()
             for i, data in enumerate(self.train_loader):
                 data = data.to(self.local_rank)
-                self.optimizer.zero_grad()
-                out, ldj = self.model(data)
-                loss = self.nll(out, ldj)
-                loss.backward()
-                self.optimizer.step()
-                if self.scheduler:
-                    self.scheduler.step()                        # per batch (main.py:223, Q15)
-                losses.append(loss.detach())
+                loss = self._graphed_step(data) if (self.cuda_graph and self.scheduler is None) else None
+                if loss is None:
+                    self.optimizer.zero_grad()
+                    out, ldj = self.model(data)
+                    loss = self.nll(out, ldj)
+                    loss.backward()
+                    self.optimizer.step()
+                    if self.scheduler:
+                        self.scheduler.step()                    # per batch (main.py:223, Q15)
+                losses.append(loss.detach().clone())
             epoch_loss = torch.stack(losses).mean()
             if self.ddp:
                 dist.all_reduce(epoch_loss, op=dist.ReduceOp.SUM)
