@@ -80,3 +80,26 @@ def test_empty_batch_is_a_no_op():
         out, ldj = model(gpu_batch(arrs), eps=torch.zeros(0, NF))
     assert out.pos.shape == (0, 3) and out.h.shape == (0, NF)
     assert float(ldj) == 0.0
+
+
+@pytest.mark.parametrize('B', [37, 75])
+def test_mid_size_train_step_vs_oracle(B):
+    """A few tiles per CTA (the software-pipelined kernels rotate three tile-info buffers and two accumulators):
+    37 molecules ~ 2 tiles of the forward and 3 of the backward kernel per CTA, 75 ~ 3-4 and 6-7; loss, latents and
+    every gradient against the oracle."""
+    from enflow_b200.data import synthetic as syn
+    from enflow_b200.flow.loss import Alchemical_NLL
+    arrs = syn.make_batch('c2', B, seed=77 + B)
+    eps = syn.make_noise(int(arrs['N'].sum()), NF, seed=5)
+    sd = syn.make_weights(NF, 128, L, seed=0)
+    model = _model()
+    out, ldj = model(gpu_batch(arrs), eps=torch.as_tensor(eps))
+    loss = Alchemical_NLL(kBT=syn.TRAIN_KBT, softening=syn.TRAIN_SOFTENING)(out, ldj)
+    loss.backward()
+    ref_loss, ref_grads, ref_state, _, _ = orc.train_step(sd, L, arrs, syn.TRAIN_DT, eps, syn.TRAIN_KBT, syn.TRAIN_SOFTENING)
+    assert abs(loss.item() - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+    for k in ('pos', 'vel', 'h', 'g'):
+        assert rel_err(to_np(getattr(out, k)), ref_state[k].detach().numpy()) < 1e-5, k
+    worst = max(np.linalg.norm(to_np(p.grad) - ref_grads[k].numpy()) / max(np.linalg.norm(ref_grads[k].numpy()), 1e-300)
+                for k, p in model.named_parameters())
+    assert worst < 1e-4, worst
