@@ -177,18 +177,9 @@ __global__ void __launch_bounds__(TPB) k_argmax_bwd(const float* __restrict__ h,
 
 __global__ void k_argmax_reduce(const float* __restrict__ partial, int n_cta, int stride, int nf,
                                 int o_w0, int o_b0, int o_w2, int o_b2, float* __restrict__ grad) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= stride) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-        a0 += partial[(int64_t)(c + 0) * stride + idx];
-        a1 += partial[(int64_t)(c + 1) * stride + idx];
-        a2 += partial[(int64_t)(c + 2) * stride + idx];
-        a3 += partial[(int64_t)(c + 3) * stride + idx];
-    }
-    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * stride + idx];
-    const float acc = (a0 + a1) + (a2 + a3);
+    int idx;
+    float acc;
+    if (!enf_reduce_partials_32x8(partial, n_cta, stride, idx, acc)) return;
     int dst;
     const int s0 = ENF_H * nf, s1 = s0 + ENF_H, s2 = s1 + 2 * nf * ENF_H;
     if (idx < s0) dst = o_w0 + idx;
@@ -282,7 +273,7 @@ int enf_argmax_bwd(const float* h, const float* eps, int N, int nf, const float*
     enf_count_launch(), k_argmax_bwd<<<grid, TPB, 0, st>>>(h, eps, N, nf, ap + o.off[PA_W0], ap + o.off[PA_B0], ap + o.off[PA_W2],
                                        ap + o.off[PA_B2], dz, dlogq, partial);
     const int stride = ENF_H * nf + ENF_H + 2 * nf * ENF_H + 2 * nf;
-    enf_count_launch(), k_argmax_reduce<<<(stride + 255) / 256, 256, 0, st>>>(partial, grid, stride, nf, (int)o.off[PA_W0],
+    enf_count_launch(), k_argmax_reduce<<<(stride + 31) / 32, 256, 0, st>>>(partial, grid, stride, nf, (int)o.off[PA_W0],
                                                            (int)o.off[PA_B0], (int)o.off[PA_W2], (int)o.off[PA_B2], agrad);
     ENF_CHECK_LAUNCH();
     return ENF_OK;

@@ -139,6 +139,33 @@ __device__ __forceinline__ double warp_sum(double v) {
 // x - rint(x/p)*p, torch.round is half-to-even (enflow/utils/helpers.py:7-8)
 __device__ __forceinline__ float wrapf_(float x, float p) { return x - rintf(x / p) * p; }
 
+// Sum of per-CTA partials for one output element, shared by the *_reduce kernels.  Launch with 256 threads and
+// ceil(stride / 32) CTAs: a block handles 32 consecutive elements x 8 CTA groups; group y adds CTAs y, y+8, ... in
+// order (coalesced 128-byte reads), the eight group sums are then added in order by the first warp.  Deterministic.
+// Returns true (with idx, acc set) for the one thread per element that must store the result.
+__device__ __forceinline__ bool enf_reduce_partials_32x8(const float* __restrict__ partial, int n_cta, int64_t stride,
+                                                         int& idx, float& acc) {
+    __shared__ float part_s[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    idx = blockIdx.x * 32 + tx;
+    float a0 = 0.f, a1 = 0.f;
+    if (idx < stride) {
+        int c = ty;
+        for (; c + 8 < n_cta; c += 16) {
+            a0 += partial[(int64_t)c * stride + idx];
+            a1 += partial[(int64_t)(c + 8) * stride + idx];
+        }
+        if (c < n_cta) a0 += partial[(int64_t)c * stride + idx];
+    }
+    part_s[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty != 0 || idx >= stride) return false;
+    acc = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) acc += part_s[y][tx];
+    return true;
+}
+
 static inline int enf_num_sms() {
     static int sms = 0;
     if (!sms) {

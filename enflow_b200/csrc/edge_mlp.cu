@@ -460,18 +460,9 @@ k_edge_bwd(const int* __restrict__ row, const int* __restrict__ col, const int* 
 // grad[dst] += sum over CTAs (fixed order)
 __global__ void k_edge_reduce(const float* __restrict__ partial, int n_cta, int o_w2, int o_w3, int o_b2, int o_b3,
                               int o_wc, int o_w1, int e1, float* __restrict__ grad) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= EDGE_PARTIAL) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // fixed order: four interleaved chains
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-        a0 += partial[(int64_t)(c + 0) * EDGE_PARTIAL + idx];
-        a1 += partial[(int64_t)(c + 1) * EDGE_PARTIAL + idx];
-        a2 += partial[(int64_t)(c + 2) * EDGE_PARTIAL + idx];
-        a3 += partial[(int64_t)(c + 3) * EDGE_PARTIAL + idx];
-    }
-    for (; c < n_cta; ++c) a0 += partial[(int64_t)c * EDGE_PARTIAL + idx];
-    const float acc = (a0 + a1) + (a2 + a3);
+    int idx;
+    float acc;
+    if (!enf_reduce_partials_32x8(partial, n_cta, EDGE_PARTIAL, idx, acc)) return;
     const int HH = ENF_H * ENF_H;
     int dst;
     if (idx < HH) dst = o_w2 + idx;
@@ -495,7 +486,7 @@ static size_t bwd_smem() { return sizeof(float) * (2 * TILE_FLOATS + 2 * KC * EN
 
 int enf_edge_reduce_partials(const float* partial, int n_cta, float* lgrad, int nf, cudaStream_t st) {
     const EgclOffsets o = enf_egcl_offsets(nf);
-    enf_count_launch(), k_edge_reduce<<<(EDGE_PARTIAL + 255) / 256, 256, 0, st>>>(
+    enf_count_launch(), k_edge_reduce<<<(EDGE_PARTIAL + 31) / 32, 256, 0, st>>>(
         partial, n_cta, (int)o.off[P_W2], (int)o.off[P_W3], (int)o.off[P_B2], (int)o.off[P_B3], (int)o.off[P_WC],
         (int)o.off[P_W1], 2 * nf + 1, lgrad);
     ENF_CHECK_LAUNCH();
@@ -545,7 +536,7 @@ int enf_edge_bwd(const int* row, const int* col, const int* rowptr, const int* E
     enf_count_launch(), k_edge_bwd<<<grid, THREADS, bwd_smem(), st>>>(row, col, rowptr, E_dev, pos, box, P, S, wr, lp + o.off[P_W2],
                                                   lp + o.off[P_W3], lp + o.off[P_WC], z2, z3, s_saved, dagg, dF,
                                                   coords_weight, dz1, dd, partial);
-    enf_count_launch(), k_edge_reduce<<<(EDGE_PARTIAL + 255) / 256, 256, 0, st>>>(partial, grid, (int)o.off[P_W2], (int)o.off[P_W3],
+    enf_count_launch(), k_edge_reduce<<<(EDGE_PARTIAL + 31) / 32, 256, 0, st>>>(partial, grid, (int)o.off[P_W2], (int)o.off[P_W3],
                                                               (int)o.off[P_B2], (int)o.off[P_B3], (int)o.off[P_WC],
                                                               (int)o.off[P_W1], 2 * nf + 1, lgrad);
     ENF_CHECK_LAUNCH();

@@ -146,9 +146,12 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
         ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
         TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, tcimg, d.nf,
                                            sv.rowptr, sv.mis, w.runs, sv.s, w.trans, st));
-        TIMED(TK_SEG128, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, sv.agg, st));
+        // agg = row sums of the run partials, F = coords_weight * row means of trans (helpers.py:62-70): one launch
+        TIMED(TK_SEG128, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, sv.agg, w.trans, 1, d.coords_weight, 0,
+                                             w.F, st));
     }
-    TIMED(TK_SEG3, enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
+    if (d.mode == 0)
+        TIMED(TK_SEG3, enf_segment_sum3(w.trans, sv.rowptr, nullptr, d.N, d.E_cap, 1, d.coords_weight, 0, w.F, st));
     if (d.mode == 0)
         TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
     else
@@ -257,12 +260,12 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
             TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
                                                sv.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
                                                w.runs, w.dz1, w.dd, lg, w.partial, st));
-            TIMED(TK_SEG128, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, st));
+            // dP and the row half of dpos (coord_diff = pos[row] - pos[col], data/base.py:17: +dd onto row atoms)
+            TIMED(TK_SEG128, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
         }
-        TIMED(TK_SEG128, enf_segment_sum128(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, st));
-        // coord_diff = pos[row] - pos[col] (data/base.py:17): +dd onto row atoms, -dd onto col atoms
-        TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
-        TIMED(TK_SEG3, enf_segment_sum3(w.dd, w.colptr, w.perm, d.N, d.E_cap, 0, -1.0f, 1, dpos, st));
+        if (d.mode == 0) TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
+        // dS and the column half of dpos (-dd onto col atoms), both through the column permutation
+        TIMED(TK_SEG128, enf_segment_sum128_sum3(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, w.dd, -1.0f, dpos, st));
         TIMED(TK_NODE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
     }
     if (eps)

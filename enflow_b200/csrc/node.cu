@@ -204,24 +204,9 @@ struct SegTable {
 // CTAs y, y+8, ... in order, the eight group sums are then added in order: deterministic and coalesced.
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partial, int n_cta, int64_t stride,
                                                           SegTable segs, float* __restrict__ grad) {
-    __shared__ float part[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int idx = blockIdx.x * 32 + tx;
-    float a0 = 0.f, a1 = 0.f;
-    if (idx < stride) {
-        int c = ty;
-        for (; c + 8 < n_cta; c += 16) {
-            a0 += partial[(int64_t)c * stride + idx];
-            a1 += partial[(int64_t)(c + 8) * stride + idx];
-        }
-        if (c < n_cta) a0 += partial[(int64_t)c * stride + idx];
-    }
-    part[ty][tx] = a0 + a1;
-    __syncthreads();
-    if (ty != 0 || idx >= stride) return;
-    float acc = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) acc += part[y][tx];
+    int idx;
+    float acc;
+    if (!enf_reduce_partials_32x8(partial, n_cta, stride, idx, acc)) return;
     int seg = -1, local = 0;
     for (int s = 0; s < segs.n; ++s)
         if (idx >= segs.src[s] && idx < segs.src[s] + segs.len[s]) { seg = s; local = idx - segs.src[s]; }

@@ -245,24 +245,9 @@ __global__ void __launch_bounds__(BT, 1) k_node_post_bwd(const float* __restrict
 __global__ void __launch_bounds__(256) k_node_post_reduce(const float* __restrict__ partial, int n_cta, int stride, int D,
                                                            int nf, int o_w4, int o_b4, int o_w5, int o_b5,
                                                            float* __restrict__ grad) {
-    __shared__ float part[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int idx = blockIdx.x * 32 + tx;
-    float a0 = 0.f, a1 = 0.f;
-    if (idx < stride) {
-        int c = ty;
-        for (; c + 8 < n_cta; c += 16) {
-            a0 += partial[(int64_t)c * stride + idx];
-            a1 += partial[(int64_t)(c + 8) * stride + idx];
-        }
-        if (c < n_cta) a0 += partial[(int64_t)c * stride + idx];
-    }
-    part[ty][tx] = a0 + a1;
-    __syncthreads();
-    if (ty != 0 || idx >= stride) return;
-    float acc = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) acc += part[y][tx];
+    int idx;
+    float acc;
+    if (!enf_reduce_partials_32x8(partial, n_cta, stride, idx, acc)) return;
     const int s0 = ENF_H * D, s1 = s0 + ENF_H, s2 = s1 + nf * ENF_H;
     int dst;
     if (idx < s0) dst = o_w4 + idx;

@@ -10,10 +10,34 @@
 
 namespace {
 
+// 3-vector segment sum of one row by one warp (lanes stride over the row's edges, xor tree): the k_segment_sum3
+// body, callable from the 128-wide kernels so a row's two reductions share one launch
+template <bool PERM>
+__device__ __forceinline__ void row_sum3(const float* __restrict__ x, const int* __restrict__ perm, int e0, int e1, int i,
+                                         int lane, int mean, float scale, int accumulate, float* __restrict__ out) {
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const int src = PERM ? perm[e] : e;
+        ax += x[(int64_t)src * 3 + 0];
+        ay += x[(int64_t)src * 3 + 1];
+        az += x[(int64_t)src * 3 + 2];
+    }
+    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+    if (lane < 3) {
+        float v = lane == 0 ? ax : (lane == 1 ? ay : az);
+        const int deg = e1 - e0;
+        if (mean) v = v / (float)(deg > 1 ? deg : 1);
+        v *= scale;
+        float* o = out + (int64_t)i * 3 + lane;
+        *o = accumulate ? (*o + v) : v;
+    }
+}
+
 template <bool SILU, bool PERM>
 __global__ void __launch_bounds__(256) k_segment_sum128(const float* __restrict__ x, const int* __restrict__ ptr,
                                                          const int* __restrict__ perm, int N, int E_cap,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, const float* __restrict__ x3,
+                                                         float scale3, float* __restrict__ out3) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps_per_grid) {
@@ -42,6 +66,7 @@ __global__ void __launch_bounds__(256) k_segment_sum128(const float* __restrict_
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         reinterpret_cast<float4*>(out + (int64_t)i * ENF_H)[lane] = acc;
+        if (x3) row_sum3<PERM>(x3, perm, e0, e1, i, lane, 0, scale3, 1, out3);      // out3 += scale3 * sum
     }
 }
 
@@ -89,7 +114,8 @@ __global__ void k_run_flags(const int* __restrict__ rowptr, int N, int* __restri
 
 __global__ void __launch_bounds__(256) k_run_sum128(const float* __restrict__ runs, const int* __restrict__ rowptr,
                                                      const int* __restrict__ mis, int N, int E_cap,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ out, const float* __restrict__ x3, int mean3,
+                                                     float scale3, int accumulate3, float* __restrict__ out3) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps_per_grid) {
@@ -105,6 +131,7 @@ __global__ void __launch_bounds__(256) k_run_sum128(const float* __restrict__ ru
             }
         }
         reinterpret_cast<float4*>(out + (int64_t)i * ENF_H)[lane] = acc;
+        if (x3) row_sum3<false>(x3, nullptr, e0, e1, i, lane, mean3, scale3, accumulate3, out3);
     }
 }
 
@@ -120,24 +147,41 @@ int enf_run_index(const int* rowptr, int N, int* mis, int* scratch, cudaStream_t
     return enf_scan_int(mis, N + 1, scratch, st);
 }
 
+int enf_run_sum128_sum3(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out,
+                        const float* x3, int mean3, float scale3, int accumulate3, float* out3, cudaStream_t st);
+int enf_segment_sum128_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
+                            const float* x3, float scale3, float* out3, cudaStream_t st);
+
 int enf_run_sum128(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out, cudaStream_t st) {
+    return enf_run_sum128_sum3(runs, rowptr, mis, N, E_cap, out, nullptr, 0, 0.f, 0, nullptr, st);
+}
+
+// the row's 128-wide run sum and (x3 != NULL) its 3-vector segment sum/mean in one launch
+int enf_run_sum128_sum3(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out,
+                        const float* x3, int mean3, float scale3, int accumulate3, float* out3, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
-    enf_count_launch(), k_run_sum128<<<blocks, 256, 0, st>>>(runs, rowptr, mis, N, E_cap, out);
+    enf_count_launch(), k_run_sum128<<<blocks, 256, 0, st>>>(runs, rowptr, mis, N, E_cap, out, x3, mean3, scale3, accumulate3, out3);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
 
 int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
                        cudaStream_t st) {
+    return enf_segment_sum128_sum3(x, ptr, perm, N, E_cap, apply_silu, out, nullptr, 0.f, nullptr, st);
+}
+
+// the 128-wide segment sum and (x3 != NULL) out3 += scale3 * the 3-vector segment sum over the same segments
+int enf_segment_sum128_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
+                            const float* x3, float scale3, float* out3, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
     if (perm) {
-        if (apply_silu) enf_count_launch(), k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
-        else enf_count_launch(), k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        if (apply_silu) enf_count_launch(), k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
+        else enf_count_launch(), k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
     } else {
-        if (apply_silu) enf_count_launch(), k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
-        else enf_count_launch(), k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out);
+        if (apply_silu) enf_count_launch(), k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
+        else enf_count_launch(), k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
     }
     ENF_CHECK_LAUNCH();
     return ENF_OK;
