@@ -456,9 +456,12 @@ __global__ void __launch_bounds__(256) k_col_fill_warp(const int* __restrict__ c
     }
 }
 
-__global__ void k_zero_int(int* __restrict__ p, int64_t n, const int* __restrict__ skip) {
+__global__ void k_zero_int2(int* __restrict__ p, int64_t n, int* __restrict__ q, int64_t m, const int* __restrict__ skip) {
     if (skip && *skip) return;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + m; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n) p[i] = 0;
+        else q[i - n] = 0;
+    }
 }
 
 // same[0] = 1 iff the two CSR edge lists are identical (used to reuse the column permutation between layers:
@@ -478,7 +481,53 @@ __global__ void k_edges_same(const int* __restrict__ ra, const int* __restrict__
 
 }  // namespace
 
+// small arrays: the whole exclusive scan in ONE CTA of 1024 threads (each thread scans a contiguous slice, one
+// block-level scan of the slice totals); element n receives the grand total like k_scan_apply
+constexpr int SCAN1_THREADS = 1024, SCAN1_MAX = 1 << 18;
+__global__ void __launch_bounds__(SCAN1_THREADS) k_scan_single(int* __restrict__ a, int n, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    __shared__ int wsum[SCAN1_THREADS / 32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int per = (n + SCAN1_THREADS - 1) / SCAN1_THREADS;
+    const int b0 = threadIdx.x * per, b1 = min(n, b0 + per);
+    int s = 0;
+    for (int i = b0; i < b1; ++i) s += a[i];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = wsum[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wsum[lane] = winc - w;                      // exclusive prefix of the warp totals
+        if (lane == 31) carry_s = winc;             // grand total
+    }
+    __syncthreads();
+    int ex = wsum[wid] + inc - s;
+    for (int i = b0; i < b1; ++i) {
+        const int v = a[i];
+        a[i] = ex;
+        ex += v;
+    }
+    if (threadIdx.x == 0) a[n] = carry_s;
+}
+
 static int scan2(int* a0, int* a1, int64_t n, int* sums, cudaStream_t st, const int* skip = nullptr) {
+    if (!a1 && n <= SCAN1_MAX) {
+        enf_count_launch(), k_scan_single<<<1, SCAN1_THREADS, 0, st>>>(a0, (int)n, skip);
+        ENF_CHECK_LAUNCH();
+        return ENF_OK;
+    }
     const int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     const int ny = a1 ? 2 : 1;
     dim3 g(nb, ny);
@@ -560,8 +609,7 @@ int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, in
     int* cursor = after_atom_mol;            // N
     int* sums = cursor + N + (N + 1);
     const int zb = enf_num_sms() * 2;
-    enf_count_launch(), k_zero_int<<<zb, 256, 0, st>>>(colptr, N + 1, skip);
-    enf_count_launch(), k_zero_int<<<zb, 256, 0, st>>>(cursor, N, skip);
+    enf_count_launch(), k_zero_int2<<<zb, 256, 0, st>>>(colptr, N + 1, cursor, N, skip);
     enf_count_launch(), k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr, skip);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(colptr, nullptr, N, sums, st, skip));

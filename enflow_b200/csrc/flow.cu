@@ -184,9 +184,13 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
         return ENF_OK;
     }
     cudaMemsetAsync(ldj_mol, 0, sizeof(float) * d.B, st);
-    for (int l = 0; l < d.L; ++l) {
-        ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
-        if (d.mode) ENF_TRY(enf_tc_pack_layer(layer_params(params, nf, l), nf, tc_image(w, l), st));
+    // weight images: the FFMA kernels' transposed fp32 copies (mode 0) or the swizzled bf16 hi/lo images of all
+    // layers in two launches (tensor-core modes)
+    if (d.mode == 0) {
+        for (int l = 0; l < d.L; ++l)
+            ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
+    } else {
+        ENF_TRY(enf_tc_pack_layers(params, nf, d.L, enf_egcl_offsets(nf).size, tc_image(w, 0), enf_tc_pack_bytes(), st));
     }
     // state entering layer 0: dequantised h (dynamics.py:11), everything else copied
     if (eps) {
@@ -287,9 +291,13 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
     const int nf = d.nf;
     if (d.B == 0 || d.N == 0) return ENF_OK;
     if (neg_ldj_mol) cudaMemsetAsync(neg_ldj_mol, 0, sizeof(float) * d.B, st);
-    for (int l = 0; l < d.L; ++l) {
-        ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
-        if (d.mode) ENF_TRY(enf_tc_pack_layer(layer_params(params, nf, l), nf, tc_image(w, l), st));
+    // weight images: the FFMA kernels' transposed fp32 copies (mode 0) or the swizzled bf16 hi/lo images of all
+    // layers in two launches (tensor-core modes)
+    if (d.mode == 0) {
+        for (int l = 0; l < d.L; ++l)
+            ENF_TRY(enf_pack_layer(layer_params(params, nf, l), nf, w.packed + (int64_t)l * enf_pack_offsets(nf).size, st));
+    } else {
+        ENF_TRY(enf_tc_pack_layers(params, nf, d.L, enf_egcl_offsets(nf).size, tc_image(w, 0), enf_tc_pack_bytes(), st));
     }
     const LayerSave& sv = w.layer[0];
     for (int l = d.L - 1; l >= 0; --l) {

@@ -77,6 +77,8 @@ int enf_lj_prior_run(double* pos, double* vel, int N, const double* box, double 
 // tensor-core (tcgen05) edge kernels; mode 1 = bf16x3 split (fp32-accurate), mode 2 = bf16
 int64_t enf_tc_pack_bytes();
 int enf_tc_pack_layer(const float* lp, int nf, unsigned char* img, cudaStream_t st);
+int enf_tc_pack_layers(const float* lp0, int nf, int L, int64_t param_stride, unsigned char* img0, int64_t img_stride,
+                       cudaStream_t st);
 int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
                     const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
                     int nf, const int* rowptr, const int* mis, float* runs, float* s_out, float* trans,

@@ -54,8 +54,10 @@ __device__ __forceinline__ void put8(unsigned char* img, uint32_t off, uint32_t 
 
 // ---- weight images (global, per layer, behind the four edge images) ------------------------------------------
 __global__ void __launch_bounds__(256) k_pack_node_tc(const float* __restrict__ W4, const float* __restrict__ W5, int nf,
-                                                       unsigned char* __restrict__ img) {
+                                                       unsigned char* __restrict__ img, int64_t param_stride,
+                                                       int64_t img_stride) {
     const int D = nf + ENF_H;
+    W4 += blockIdx.y * param_stride; W5 += blockIdx.y * param_stride; img += blockIdx.y * img_stride;     // blockIdx.y = layer
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     float x[8];
     unsigned char* dst;
@@ -458,9 +460,11 @@ int tc_grid(int N) {
 
 int enf_node_post_reduce(const float* partial, int n_cta, int nf, float* lgrad, cudaStream_t st);
 
-int enf_node_tc_pack(const float* lp, int nf, unsigned char* img, cudaStream_t st) {
+int enf_node_tc_pack(const float* lp0, int nf, int L, int64_t param_stride, unsigned char* img0, int64_t img_stride,
+                     cudaStream_t st) {
     const EgclOffsets o = enf_egcl_offsets(nf);
-    enf_count_launch(), k_pack_node_tc<<<(PACK_ITEMS + 255) / 256, 256, 0, st>>>(lp + o.off[P_W4], lp + o.off[P_W5], nf, img);
+    enf_count_launch(), k_pack_node_tc<<<dim3((PACK_ITEMS + 255) / 256, L), 256, 0, st>>>(lp0 + o.off[P_W4], lp0 + o.off[P_W5], nf,
+                                                                                      img0, param_stride, img_stride);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }
