@@ -24,11 +24,62 @@ constexpr int TE = 64;                     // edges per tile
 constexpr int ACT_IMG = 128 * TE * 2;      // one bf16 activation image: 16 KB
 constexpr uint32_t T1_COL = 0, T2_COL = 64, TW2_COL = 128, TW3_COL = 256, T1B_COL = 384, TMEM_COLS = 512;   // T1 alternates per tile
 
+// Per-tile record.  The first GEOM_BYTES are produced for every tile by k_edge_geom_bwd (one fully parallel pass over
+// the edges) and arrive in shared memory by one TMA bulk copy two tiles ahead; dr_part is kernel-local scratch.
 struct TileInfoB {
     int row[TE], col[TE], valid[TE], start[TE], mis[TE];
     float d[TE][3], r[TE], ds[TE], ddir[TE][3];
     float dr_part[4][TE];
 };
+constexpr int GEOM_BYTES = 13 * TE * 4;
+static_assert(offsetof(TileInfoB, dr_part) == GEOM_BYTES && GEOM_BYTES % 16 == 0 && sizeof(TileInfoB) % 16 == 0, "tile record layout");
+
+// per-edge geometry and the force-branch seed (enflow/data/base.py:15-19, egcl.py:71-75 differentiated): padding edges of
+// the last tile are self-edges of atom 0 with zero seeds
+__global__ void __launch_bounds__(256) k_edge_geom_bwd(const int* __restrict__ row, const int* __restrict__ col,
+                                                        const int* __restrict__ rowptr, const int* __restrict__ E_dev,
+                                                        const float* __restrict__ pos, const float* __restrict__ box,
+                                                        const float* __restrict__ s_saved, const float* __restrict__ dF,
+                                                        float coords_weight, const int* __restrict__ mis,
+                                                        unsigned char* __restrict__ geom) {
+    const int E = E_dev[0];
+    const int slots = (E + TE - 1) / TE * TE;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < slots; e += gridDim.x * blockDim.x) {
+        const bool ok = e < E;
+        int i = 0, j = 0;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, ds = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        int start = 0, m = 0;
+        if (ok) {
+            i = row[e]; j = col[e];
+            d0 = wrapf_(pos[(int64_t)i * 3 + 0] - pos[(int64_t)j * 3 + 0], 0.5f * box[(int64_t)i * 3 + 0]);
+            d1 = wrapf_(pos[(int64_t)i * 3 + 1] - pos[(int64_t)j * 3 + 1], 0.5f * box[(int64_t)i * 3 + 1]);
+            d2 = wrapf_(pos[(int64_t)i * 3 + 2] - pos[(int64_t)j * 3 + 2], 0.5f * box[(int64_t)i * 3 + 2]);
+            const int r0 = rowptr[i];
+            const int deg = rowptr[i + 1] - r0;
+            const float sc = coords_weight / (float)(deg > 1 ? deg : 1);          // helpers.py:70 (Q12)
+            const float s = s_saved[e];
+            const float dv[3] = {d0, d1, d2};
+            float dtr[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float tr = dv[c] * s;
+                const bool pass = (tr >= -100.f) && (tr <= 100.f);               // clamp backward mask
+                dtr[c] = pass ? dF[(int64_t)i * 3 + c] * sc : 0.f;
+                ds = fmaf(dtr[c], dv[c], ds);
+            }
+            q0 = dtr[0] * s; q1 = dtr[1] * s; q2 = dtr[2] * s;
+            start = e == r0;
+            m = mis[i + 1];
+        }
+        TileInfoB& ti = *reinterpret_cast<TileInfoB*>(geom + (int64_t)(e / TE) * GEOM_BYTES);     // only the record part exists
+        const int t = e % TE;
+        ti.row[t] = i; ti.col[t] = j; ti.valid[t] = ok; ti.start[t] = start; ti.mis[t] = m;
+        ti.d[t][0] = d0; ti.d[t][1] = d1; ti.d[t][2] = d2;
+        ti.r[t] = d0 * d0 + d1 * d1 + d2 * d2;
+        ti.ds[t] = ds;
+        ti.ddir[t][0] = q0; ti.ddir[t][1] = q1; ti.ddir[t][2] = q2;
+    }
+}
 
 template <bool SPLIT>
 struct SmemB {
@@ -86,14 +137,12 @@ constexpr int EDGE_PARTIAL = 2 * ENF_H * ENF_H + 4 * ENF_H;
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ rowptr,
-              const int* __restrict__ E_dev, const float* __restrict__ pos, const float* __restrict__ box,
+k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_dev,
               const float* __restrict__ P, const float* __restrict__ S, const float* __restrict__ W1, int e1,
               const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ wc,
-              const unsigned char* __restrict__ wimg, const float* __restrict__ s_saved,
-              const float* __restrict__ dagg, const float* __restrict__ dF, float coords_weight,
-              const int* __restrict__ mis, float* __restrict__ runs, float* __restrict__ dz1,
-              float* __restrict__ dd_out, float* __restrict__ partial) {
+              const unsigned char* __restrict__ wimg, const float* __restrict__ dagg,
+              float* __restrict__ runs, float* __restrict__ dz1, float* __restrict__ dd_out,
+              float* __restrict__ partial) {
     using L = SmemB<SPLIT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024 - (tc::smem_u32(smem_raw) & 1023)) & 1023);
@@ -105,7 +154,8 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     uint64_t* bar_mma = bar_w + 1;
     uint64_t* bar_wg = bar_w + 2;          // the weight-gradient MMAs of a phase have completed (operands reusable)
     uint64_t* bar_g1 = bar_w + 3;          // the first GEMM of a tile is issued one tile ahead: its own barrier
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
+    uint64_t* bar_geom = bar_w + 4;        // tile records arriving by TMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 5);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = w & 3, cg = w >> 2;
@@ -117,6 +167,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         tc::mbar_init(bar_mma, 1);
         tc::mbar_init(bar_wg, 1);
         tc::mbar_init(bar_g1, 1);
+        tc::mbar_init(bar_geom, 1);
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -179,40 +230,15 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);
         }
     };
-    // per-edge geometry and the force-branch seed of one tile, by the first TE threads
-    auto geometry = [&](TileInfoB& ti, int e0) {
-        if (tid < TE) {
-            const int e = e0 + tid;
-            const bool ok = e < E;
-            int i = 0, j = 0;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, ds = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
-            if (ok) {
-                i = row[e]; j = col[e];
-                d0 = wrapf_(pos[(int64_t)i * 3 + 0] - pos[(int64_t)j * 3 + 0], 0.5f * box[(int64_t)i * 3 + 0]);
-                d1 = wrapf_(pos[(int64_t)i * 3 + 1] - pos[(int64_t)j * 3 + 1], 0.5f * box[(int64_t)i * 3 + 1]);
-                d2 = wrapf_(pos[(int64_t)i * 3 + 2] - pos[(int64_t)j * 3 + 2], 0.5f * box[(int64_t)i * 3 + 2]);
-                const int deg = rowptr[i + 1] - rowptr[i];
-                const float sc = coords_weight / (float)(deg > 1 ? deg : 1);          // helpers.py:70 (Q12)
-                const float s = s_saved[e];
-                const float dv[3] = {d0, d1, d2};
-                float dtr[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float tr = dv[c] * s;
-                    const bool pass = (tr >= -100.f) && (tr <= 100.f);               // clamp backward mask
-                    dtr[c] = pass ? dF[(int64_t)i * 3 + c] * sc : 0.f;
-                    ds = fmaf(dtr[c], dv[c], ds);
-                }
-                q0 = dtr[0] * s; q1 = dtr[1] * s; q2 = dtr[2] * s;
-            }
-            ti.row[tid] = i; ti.col[tid] = j; ti.valid[tid] = ok;
-            ti.start[tid] = ok && (e == rowptr[i]);
-            ti.mis[tid] = ok ? mis[i + 1] : 0;
-            ti.d[tid][0] = d0; ti.d[tid][1] = d1; ti.d[tid][2] = d2;
-            ti.r[tid] = d0 * d0 + d1 * d1 + d2 * d2;
-            ti.ds[tid] = ds;
-            ti.ddir[tid][0] = q0; ti.ddir[tid][1] = q1; ti.ddir[tid][2] = q2;
-        }
+    // the record of one tile (k_edge_geom_bwd) into a TileInfoB, asynchronously, by one thread
+    auto fetch_tile = [&](TileInfoB& ti, int tile) {
+        tc::mbar_expect_tx(bar_geom, GEOM_BYTES);
+        tc::bulk_g2s(&ti, geom + (int64_t)tile * GEOM_BYTES, GEOM_BYTES, bar_geom);
+    };
+    uint32_t parity_geom = 0;
+    auto wait_tile = [&]() {
+        tc::mbar_wait(bar_geom, parity_geom);
+        parity_geom ^= 1;
     };
     auto issue_mma = [&](auto&& body, bool commit = true) {          // one thread issues
         tc::fence_async_smem();
@@ -253,9 +279,12 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     float z1[16];
     const int stride = gridDim.x;
     if ((int)blockIdx.x < tiles) {
-        geometry(tib[0], blockIdx.x * TE);
-        if ((int)blockIdx.x + stride < tiles) geometry(tib[1], (blockIdx.x + stride) * TE);
-        __syncthreads();
+        if (tid == 0) fetch_tile(tib[0], blockIdx.x);
+        wait_tile();
+        if ((int)blockIdx.x + stride < tiles) {
+            if (tid == 0) fetch_tile(tib[1], blockIdx.x + stride);
+            wait_tile();
+        }
         load_z1(tib[0], z1);
         put_x1(z1, nullptr);
         issue_g1(t1col);
@@ -266,6 +295,10 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         TileInfoB& tn = tib[cur == 2 ? 0 : cur + 1];
         TileInfoB& tnn = tib[cur == 0 ? 2 : cur - 1];
         const int next = tile + stride, next2 = next + stride;
+        // the next tile's record was requested one iteration ago (the first two in the prologue).  Everybody observes
+        // its arrival HERE, before the barrier in front of the next request: an mbarrier must not run two phases
+        // ahead of a waiter.
+        if (tile != (int)blockIdx.x && next < tiles) wait_tile();
         // ---- T1 = W2 x1^T (issued one tile ahead)
         tc::mbar_wait(bar_g1, parity_g1);
         parity_g1 ^= 1;
@@ -289,7 +322,7 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         }
         // ---- T2 = W3 x2^T
         issue_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T2_COL, dW3k, WLO, dXTm, ALO, id_kmn64, false); });
-        if (next2 < tiles) geometry(tnn, next2 * TE);
+        if (next2 < tiles && tid == 0) fetch_tile(tnn, next2);        // two tiles ahead; waited for before its first use
         wait_mma();
         {
             float v[16];
@@ -434,11 +467,14 @@ k_edge_bwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 
 int enf_edge_reduce_partials(const float* partial, int n_cta, float* lgrad, int nf, cudaStream_t st);
 
+// bytes of the per-tile records k_edge_geom_bwd writes for a capacity of E_cap edges (16-byte aligned buffer)
+int64_t enf_edge_bwd_geom_bytes(int E_cap) { return ((int64_t)(E_cap + TE - 1) / TE + 1) * GEOM_BYTES; }
+
 int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
                     const float* pos, const float* box, const float* P, const float* S, const float* lp,
                     const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
                     float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
-                    float* partial, cudaStream_t st) {
+                    float* partial, unsigned char* geom, cudaStream_t st) {
     if (E_cap == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const int grid = enf_num_sms();
@@ -448,14 +484,18 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
         cudaFuncSetAttribute(k_edge_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemB<false>::total);
         attr = true;
     }
+    const int slots = (E_cap + TE - 1) / TE * TE;
+    int ggrid = (slots + 255) / 256;
+    if (ggrid > 8 * enf_num_sms()) ggrid = 8 * enf_num_sms();
+    enf_count_launch(), k_edge_geom_bwd<<<ggrid, 256, 0, st>>>(row, col, rowptr, E_dev, pos, box, s_saved, dF, coords_weight, mis, geom);
     if (mode == 1)
         enf_count_launch(), k_edge_bwd_tc<true><<<grid, THREADS, SmemB<true>::total, st>>>(
-            row, col, rowptr, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
-            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, mis, runs, dz1, dd, partial);
+            geom, E_dev, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3], lp + o.off[P_WC], wimg, dagg,
+            runs, dz1, dd, partial);
     else
         enf_count_launch(), k_edge_bwd_tc<false><<<grid, THREADS, SmemB<false>::total, st>>>(
-            row, col, rowptr, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
-            lp + o.off[P_WC], wimg, s_saved, dagg, dF, coords_weight, mis, runs, dz1, dd, partial);
+            geom, E_dev, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3], lp + o.off[P_WC], wimg, dagg,
+            runs, dz1, dd, partial);
     ENF_CHECK_LAUNCH();
     return enf_edge_reduce_partials(partial, grid, lgrad, nf, st);
 }

@@ -52,6 +52,7 @@ struct Workspace {
     float* log_q;
     // backward scratch
     float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd, *partial, *Qscratch;
+    unsigned char* geom;     // per-tile edge records of the tensor-core backward kernel
     int *colptr, *perm, *same;
     size_t bytes;
 };
@@ -101,6 +102,7 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
         w.dz1 = b.take<float>(E * H); w.dd = b.take<float>(E * 3);
         w.partial = b.take<float>(partial_floats(d));
         w.Qscratch = b.take<float>(N);
+        w.geom = d.mode ? b.take<unsigned char>((size_t)enf_edge_bwd_geom_bytes(d.E_cap)) : nullptr;
         w.colptr = b.take<int>(N + 1); w.perm = b.take<int>(E); w.same = b.take<int>(4);
     }
     w.bytes = (b.off + 255) / 256 * 256;
@@ -263,7 +265,7 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         } else {
             TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
                                                sv.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
-                                               w.runs, w.dz1, w.dd, lg, w.partial, st));
+                                               w.runs, w.dz1, w.dd, lg, w.partial, w.geom, st));
             // dP and the row half of dpos (coord_diff = pos[row] - pos[col], data/base.py:17: +dd onto row atoms)
             TIMED(TK_SEG128, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
         }
