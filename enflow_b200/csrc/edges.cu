@@ -481,43 +481,60 @@ __global__ void k_edges_same(const int* __restrict__ ra, const int* __restrict__
 
 }  // namespace
 
-// small arrays: the whole exclusive scan in ONE CTA of 1024 threads (each thread scans a contiguous slice, one
-// block-level scan of the slice totals); element n receives the grand total like k_scan_apply
+// small arrays: the whole exclusive scan in ONE CTA of 1024 threads, 4096 elements per pass (coalesced 16-byte
+// loads, warp scans, one carry); element n receives the grand total like k_scan_apply
 constexpr int SCAN1_THREADS = 1024, SCAN1_MAX = 1 << 18;
 __global__ void __launch_bounds__(SCAN1_THREADS) k_scan_single(int* __restrict__ a, int n, const int* __restrict__ skip) {
     if (skip && *skip) return;
     __shared__ int wsum[SCAN1_THREADS / 32];
     __shared__ int carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int per = (n + SCAN1_THREADS - 1) / SCAN1_THREADS;
-    const int b0 = threadIdx.x * per, b1 = min(n, b0 + per);
-    int s = 0;
-    for (int i = b0; i < b1; ++i) s += a[i];
-    int inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[wid] = inc;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (wid == 0) {
-        int w = wsum[lane];
-        int winc = w;
+    const bool vec = (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+    for (int base = 0; base < n; base += SCAN1_THREADS * 4) {
+        const int i = base + threadIdx.x * 4;
+        int v[4] = {0, 0, 0, 0};
+        if (vec && i + 3 < n) {
+            const int4 q = *reinterpret_cast<const int4*>(a + i);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i + k < n) v[k] = a[i + k];
+        }
+        const int s = v[0] + v[1] + v[2] + v[3];
+        int inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-        wsum[lane] = winc - w;                      // exclusive prefix of the warp totals
-        if (lane == 31) carry_s = winc;             // grand total
-    }
-    __syncthreads();
-    int ex = wsum[wid] + inc - s;
-    for (int i = b0; i < b1; ++i) {
-        const int v = a[i];
-        a[i] = ex;
-        ex += v;
+        const int carry = carry_s;                  // read before the barrier: warp 0 updates it after
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int w = wsum[lane];
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wsum[lane] = winc - w;                  // exclusive prefix of the warp totals
+            if (lane == 31) carry_s = carry + winc;
+        }
+        __syncthreads();
+        int ex = carry + wsum[wid] + inc - s;
+        if (vec && i + 3 < n) {
+            *reinterpret_cast<int4*>(a + i) = make_int4(ex, ex + v[0], ex + v[0] + v[1], ex + v[0] + v[1] + v[2]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i + k < n) a[i + k] = ex;
+                ex += v[k];
+            }
+        }
+        __syncthreads();                            // wsum / carry_s are rewritten by the next pass
     }
     if (threadIdx.x == 0) a[n] = carry_s;
 }
