@@ -330,8 +330,8 @@ def main():
             tc_mode = args.precision != 'fp32'
             kname = 'k_' + dom + ('_tc' if tc_mode else '')
             # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
-            # (profiles/r1b_tc_kernels_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
-            traffic = {'k_edge_bwd_tc': 497.6e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
+            # (profiles/r1c_edge_kernels_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
+            traffic = {'k_edge_bwd_tc': 528.5e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
             mma_per_gemm = {'fp32': 0, 'fp32_tc': 3, 'bf16': 1}[args.precision]
             roof = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'],
                     'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'], 'traffic': traffic,

@@ -17,6 +17,20 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// Debug builds (make PHASE=1): clock64 stamps at the phase boundaries of four tiles of one CTA, read back by
+// tools/phase_times.py.  Not part of the product library (the extra symbol is not in include/enflow_b200.h).
+#ifdef ENF_PHASE_TIMING
+__device__ long long g_phase[4 * 16];
+#define STAMP(k) do { if (blockIdx.x == 3 && tid == 37 && tile_no >= 8 && tile_no < 12) g_phase[(tile_no - 8) * 16 + (k)] = clock64(); } while (0)
+#pragma GCC visibility push(default)
+extern "C" int enflow_debug_phase_times(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_phase, sizeof(long long) * 64);
+}
+#pragma GCC visibility pop
+#else
+#define STAMP(k)
+#endif
+
 namespace {
 
 constexpr int THREADS = 512;
@@ -289,7 +303,10 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
         put_x1(z1, nullptr);
         issue_g1(t1col);
     }
+    int tile_no = -1;
     for (int tile = blockIdx.x; tile < tiles; tile += stride) {
+        ++tile_no;
+        STAMP(0);
         const int e0 = tile * TE;
         TileInfoB& ti = tib[cur];
         TileInfoB& tn = tib[cur == 2 ? 0 : cur + 1];
@@ -303,6 +320,7 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
         tc::mbar_wait(bar_g1, parity_g1);
         parity_g1 ^= 1;
         tc::fence_after_sync();
+        STAMP(1);
         float dsl2[16];                 // silu'(z2), consumed two phases later
         {
             tc::tmem_ld16(lane_base + t1col + ec, dsl2);
@@ -320,10 +338,13 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
                 store8<SPLIT>(XB, t_off_(n, 2 * cg + ch), x);          // x2^T image [k][e] over x1^T
             }
         }
+        STAMP(2);
         // ---- T2 = W3 x2^T
         issue_mma([&]() { tc::issue_gemm_t<SPLIT, 8, tc::OffK128, tc::OffMN>(tmem + T2_COL, dW3k, WLO, dXTm, ALO, id_kmn64, false); });
+        STAMP(3);
         if (next2 < tiles && tid == 0) fetch_tile(tnn, next2);        // two tiles ahead; waited for before its first use
         wait_mma();
+        STAMP(4);
         {
             float v[16];
             tc::tmem_ld16(lane_base + T2_COL + ec, v);
@@ -345,6 +366,7 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
                 store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz3^T image [n][e]
             }
         }
+        STAMP(5);
         // ---- TW3 += dz3^T x2 ; T2 = W3^T dz3^T   (while the tensor pipe runs: gather dagg)
         issue_mma([&]() {
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + T2_COL, dW3m, WLO, dZm, ALO, id_mm64, false);
@@ -352,11 +374,14 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
             tc::issue_gemm_t<SPLIT, 4, tc::OffK, tc::OffK>(tmem + TW3_COL, dZk, ALO, dXk, ALO, id_kk128, !first_tile);
             tc::mma_commit(bar_wg);              // ... the wgrad finishes behind it
         }, false);
+        STAMP(6);
         float da[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             da[j] = ti.valid[ec + j] ? __ldg(dagg + (int64_t)ti.row[ec + j] * ENF_H + n) : 0.f;
+        STAMP(7);
         wait_mma();
+        STAMP(8);
         {
             float v[16];
             tc::tmem_ld16(lane_base + T2_COL + ec, v);
@@ -374,8 +399,10 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
                 store8<SPLIT>(ZB, t_off_(n, 2 * cg + ch), x);          // dz2^T image [n][e]
             }
         }
+        STAMP(9);
         float ds1[16];
-        put_x1(z1, ds1);                                                // x2^T is dead: rebuild x1^T, keep silu'(z1)
+        put_x1(z1, ds1);
+        STAMP(10);                                                // x2^T is dead: rebuild x1^T, keep silu'(z1)
         // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   
         issue_mma([&]() {
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + t1col, dW2m, WLO, dZm, ALO, id_mm64, false);
@@ -384,13 +411,17 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
             tc::mma_commit(bar_wg);              // waited for before x1^T is rewritten (below, or after the last tile)
         }, false);
         first_tile = false;
-        if (next < tiles) load_z1(tn, z1);                              // next tile's gather, behind the MMAs
+        STAMP(11);
+        if (next < tiles) load_z1(tn, z1);
+        STAMP(12);                              // next tile's gather, behind the MMAs
         wait_mma();
+        STAMP(13);
         if (next < tiles) {                  // next tile's x1^T and its first MMA, which then runs under the epilogue
             wait_wgrad();
             put_x1(z1, nullptr);
             issue_g1(T1B_COL - t1col);
         }
+        STAMP(14);
         {
             float v[16];
             tc::tmem_ld16(lane_base + t1col + ec, v);
@@ -423,6 +454,7 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
 #pragma unroll
             for (int c = 0; c < 3; ++c) dd_out[(int64_t)(e0 + tid) * 3 + c] = fmaf(dr2, ti.d[tid][c], ti.ddir[tid][c]);
         }
+        STAMP(15);
         cur = cur == 2 ? 0 : cur + 1;
         t1col = T1B_COL - t1col;
     }

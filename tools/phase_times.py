@@ -1,4 +1,8 @@
-"""Debug only: read the clock64 stamps of a -DENF_PHASE_TIMING build of k_edge_bwd_tc."""
+"""Debug only: clock64 phase timeline of k_edge_bwd_tc (profiles/r1c_phase_times.txt).
+
+    make -C enflow_b200/csrc clean && make -C enflow_b200/csrc PHASE=1 && python tools/phase_times.py
+    make -C enflow_b200/csrc clean && make -C enflow_b200/csrc          # back to the product library
+"""
 import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
