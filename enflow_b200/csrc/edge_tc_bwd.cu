@@ -401,8 +401,13 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
         }
         STAMP(9);
         float ds1[16];
-        put_x1(z1, ds1);
-        STAMP(10);                                                // x2^T is dead: rebuild x1^T, keep silu'(z1)
+        put_x1(z1, ds1);                                          // x2^T is dead: rebuild x1^T, keep silu'(z1)
+        STAMP(10);
+        // z1's registers are free: request the next tile's S rows before the barrier in front of the MMA issue
+        if (next < tiles) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z1[j] = __ldg(S + (int64_t)tn.col[ec + j] * ENF_H + n);
+        }
         // ---- TW2 += dz2^T x1 ; T1 = W2^T dz2^T   
         issue_mma([&]() {
             tc::issue_gemm_t<SPLIT, 8, tc::OffMN, tc::OffMN>(tmem + t1col, dW2m, WLO, dZm, ALO, id_mm64, false);
@@ -412,7 +417,11 @@ k_edge_bwd_tc(const unsigned char* __restrict__ geom, const int* __restrict__ E_
         }, false);
         first_tile = false;
         STAMP(11);
-        if (next < tiles) load_z1(tn, z1);
+        if (next < tiles) {                                             // rest of the next tile's gather, behind the MMAs
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                z1[j] = fmaf(wrn, tn.r[ec + j], __ldg(P + (int64_t)tn.row[ec + j] * ENF_H + n) + z1[j]);
+        }
         STAMP(12);                              // next tile's gather, behind the MMAs
         wait_mma();
         STAMP(13);
