@@ -51,7 +51,7 @@ struct Workspace {
     double* logq_mol;
     float* log_q;
     // backward scratch
-    float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd, *partial, *Qscratch;
+    float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd, *partial;
     unsigned char* geom;     // per-tile edge records of the tensor-core backward kernel
     int *colptr, *perm, *same;
     size_t bytes;
@@ -101,7 +101,6 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
         w.dagg = b.take<float>(N * H); w.dP = b.take<float>(N * H); w.dS = b.take<float>(N * H);
         w.dz1 = b.take<float>(E * H); w.dd = b.take<float>(E * 3);
         w.partial = b.take<float>(partial_floats(d));
-        w.Qscratch = b.take<float>(N);
         w.geom = d.mode ? b.take<unsigned char>((size_t)enf_edge_bwd_geom_bytes(d.E_cap)) : nullptr;
         w.colptr = b.take<int>(N + 1); w.perm = b.take<int>(E); w.same = b.take<int>(4);
     }
