@@ -12,8 +12,11 @@
 //                  (hi.hi + lo.hi + hi.lo) accumulated in fp32: end-to-end drift <= 1.3e-7 on the latents.
 //   SPLIT = false: bf16 operands, one MMA per GEMM (the north star's "bf16 MLP" mode, tolerance 1e-2).
 //
-// Thread map: 16 warps. warp w owns TMEM lanes / edge rows [32 (w%4), +32) (the hardware's lane-quarter rule)
-// and feature columns [32 (w/4), +32): every thread handles one edge row x 32 columns in all phases.
+// Thread map: 16 warps.  Accumulators are transposed (TMEM lane = hidden unit n, column = edge): warp w owns
+// TMEM lanes [32 (w%4), +32) (the hardware's lane-quarter rule) and tile edges [32 (w/4), +32), i.e. in the epilogues
+// every thread handles one hidden unit x 32 consecutive edges; x1 is produced one warp per edge row.
+// Tiles are software-pipelined per CTA (geometry two tiles ahead, z1 gather and first MMA one tile ahead), see the
+// comment in front of the tile loop and profiles/r1c_phase_times.txt.
 #include "common.cuh"
 #include "tc_common.cuh"
 

@@ -14,6 +14,8 @@
 // (hi/lo images) shared memory holds the two weight matrices (128 KB) plus two activation buffers (64 KB).
 //
 // Thread map: 16 warps; warp w owns TMEM lanes [32 (w%4), +32) = hidden units n and tile edges [16 (w/4), +16).
+// Tiles are software-pipelined per CTA: per-tile edge records (k_edge_geom_bwd) arrive by TMA two tiles ahead, the z1
+// gather and the first MMA of tile t+1 are issued during tile t (profiles/r1c_phase_times.txt).
 #include "common.cuh"
 #include "tc_common.cuh"
 
