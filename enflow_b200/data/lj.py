@@ -26,14 +26,19 @@ from .base import Data
 
 
 def arrange_points_on_grid(n, box, gap):
-    """n points on a regular grid inside [gap, box - gap]^3 (`enflow/data/lj.py:9-30`: same counts per axis and the
-    same x-fastest-within-y ordering of `np.meshgrid(x, y, z)` flattened)."""
-    num_z = int(np.ceil(n ** (1 / 3)))
-    num_y = int(np.ceil((n / num_z) ** (1 / 2)))
-    num_x = int(np.ceil(n / (num_y * num_z)))
-    axes = [np.linspace(gap, box[k] - gap, m) for k, m in enumerate((num_x, num_y, num_z))]
-    grid = np.meshgrid(*axes)
-    return np.stack([g.flatten() for g in grid], axis=-1)[:n]
+    """The first n sites of a regular lattice spanning [gap, box - gap] on every axis: the start configuration of
+    the reference's run (`enflow/data/lj.py:9-30`).  Sites per axis follow the reference (z: ceil(n^(1/3)), then y,
+    then x) and the sites are enumerated z fastest, then x, then y, which is the order its flattened meshgrid has."""
+    nz = int(np.ceil(n ** (1.0 / 3.0)))
+    ny = int(np.ceil(np.sqrt(n / nz)))
+    nx = int(np.ceil(n / (ny * nz)))
+    site = np.arange(n)
+    index = {2: site % nz, 0: (site // nz) % nx, 1: site // (nz * nx)}
+    out = np.empty((n, 3), dtype=np.float64)
+    for axis, count in ((0, nx), (1, ny), (2, nz)):
+        step = (box[axis] - 2.0 * gap) / (count - 1) if count > 1 else 0.0
+        out[:, axis] = gap + step * index[axis]
+    return out
 
 
 class LJDataset:
