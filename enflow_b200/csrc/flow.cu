@@ -264,7 +264,7 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         } else {
             TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
                                                sv.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
-                                               w.runs, w.dz1, w.dd, lg, w.partial, w.geom, st));
+                                               w.runs, w.dz1, w.dd, lg, w.partial, w.geom, status, st));
             // dP and the row half of dpos (coord_diff = pos[row] - pos[col], data/base.py:17: +dd onto row atoms)
             TIMED(TK_SEG128, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
         }
@@ -276,7 +276,6 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
     if (eps)
         TIMED(TK_ARGMAX, enf_argmax_bwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), dh, dldj,
                                argmax_params(grads, nf, d.L), w.partial, st));
-    (void)status;
     return ENF_OK;
 }
 

@@ -87,7 +87,7 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
                     const float* pos, const float* box, const float* P, const float* S, const float* lp,
                     const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
                     float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
-                    float* partial, unsigned char* geom, cudaStream_t st);
+                    float* partial, unsigned char* geom, int* status, cudaStream_t st);
 int64_t enf_edge_bwd_geom_bytes(int E_cap);
 // tensor-core node_model (node_tc.cu); weight images live behind the edge images in the same per-layer buffer
 int enf_node_post_fwd_tc(int mode, const float* h, const float* agg, int N, int nf, const float* lp,

@@ -106,6 +106,45 @@ template <bool SPLIT, int KS, typename OA, typename OB>
 __device__ __forceinline__ void issue_gemm_t(uint32_t tmem_d, uint64_t a, uint32_t a_lo_bytes, uint64_t b,
                                              uint32_t b_lo_bytes, uint32_t idesc, bool acc_first);
 
+// exactly one lane of the (converged) warp gets true
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Compact issue loop for a dedicated MMA-issuing warp: the whole warp runs the (uniform) loop and address arithmetic,
+// only the tcgen05.mma itself is predicated on `leader` (from elect_one).  One GEMM = 1 (bf16) or 3 (bf16x3 split)
+// passes over NBLK blocks of four k-steps; k-step (blk, i) of an operand is at blk * BLK + i * IN bytes.
+// Small code (a few dozen instructions per call site) matters: the fully unrolled form of a 10-GEMM tile loop is
+// ~100 KB of straight-line code that is executed once per pass and misses the instruction cache on every line.
+template <bool SPLIT, int NBLK, uint32_t A_BLK, uint32_t A_IN, uint32_t B_BLK, uint32_t B_IN>
+__device__ __forceinline__ void issue_gemm_loop(bool leader, uint32_t tmem_d, uint64_t a, uint32_t a_lo_bytes, uint64_t b,
+                                                uint32_t b_lo_bytes, uint32_t idesc, bool acc_first) {
+    constexpr int NP = SPLIT ? 3 : 1;
+#pragma unroll 1
+    for (int p = 0; p < NP; ++p) {
+        uint64_t ap = a + (uint64_t)((p == 2 ? a_lo_bytes : 0u) >> 4);
+        uint64_t bp = b + (uint64_t)((p == 1 ? b_lo_bytes : 0u) >> 4);
+#pragma unroll 1
+        for (int blk = 0; blk < NBLK; ++blk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool acc = acc_first || p > 0 || blk > 0 || i > 0;
+                if (leader) mma_f16(tmem_d, ap + (uint64_t)((i * A_IN) >> 4), bp + (uint64_t)((i * B_IN) >> 4), idesc, acc);
+            }
+            ap += (uint64_t)(A_BLK >> 4);
+            bp += (uint64_t)(B_BLK >> 4);
+        }
+    }
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {      // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
@@ -146,7 +185,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// registers -> TMEM, same shape as tmem_ld16 (per-thread scratch in spare accumulator columns); completes before return
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
