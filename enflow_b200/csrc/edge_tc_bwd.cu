@@ -245,7 +245,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
         tc::mbar_init(bar_w, 1);
         for (int p = 0; p < 2; ++p) {
             tc::mbar_init(bar_acc + p, 1);
-            tc::mbar_init(bar_opnd + p, EPI_THREADS);
+            tc::mbar_init(bar_opnd + p, EPI_THREADS / 32);          // one arrival per epilogue warp
             tc::mbar_init(bar_wgd + p, 1);
         }
         for (int s = 0; s < RING; ++s) tc::mbar_init(bar_idx + s, 1);
@@ -354,16 +354,21 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
         float sa[16], sb[16];                  // per-pipeline state: z1 of the pipeline's tile, from its gather to E3
 
         int kq = -1, tq = 0;                    // (debug stamps only)
+        // mbarrier arrivals go through the same L1/shared-memory data pipe as the MMA operand reads, and 32 lanes arriving
+        // on one barrier word are 32 serialised accesses (ncu: the per-thread form was 15 % of that pipe): one lane per
+        // warp arrives, __syncwarp orders the other lanes' writes before it
+        auto wait_bar = [&](uint64_t* bar, uint32_t parity) { tc::mbar_wait(bar, parity); };
         auto wait_acc = [&](int p, uint32_t parity) {
             STAMP_E(kq, 3 * tq);
-            tc::mbar_wait(bar_acc + p, parity);
+            wait_bar(bar_acc + p, parity);
             tc::fence_after_sync();
             STAMP_E(kq, 3 * tq + 1);
         };
-        auto arrive = [&](int p) {             // this thread's operand writes and TMEM reads of the task are done
+        auto arrive = [&](int p) {             // this warp's operand writes and TMEM reads of the task are done
             tc::fence_before_sync();
             tc::fence_async_smem();
-            tc::mbar_arrive(bar_opnd + p);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bar_opnd + p);
             STAMP_E(kq, 3 * tq + 2);
         };
         // z1 = P[row] + S[col] + w_r r for this thread's (hidden unit, 16 edges); row reads coalesce over the 32 hidden
@@ -373,7 +378,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
         // order makes most of the row requests repeats.
         auto gather_z1 = [&](int t, float (&z)[16]) {
             const int s = t % RING;
-            tc::mbar_wait(bar_idx + s, (uint32_t)(t / RING) & 1);
+            wait_bar(bar_idx + s, (uint32_t)(t / RING) & 1);
             const int* ir = ring + s * IDX_INTS + ec;
             const int bits = ring[s * IDX_INTS + 2 * TE + 2 * cg + 1];
             const float4* r4 = reinterpret_cast<const float4*>(gv.r + (int64_t)(cta + t * G) * TE + ec);
@@ -482,7 +487,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
                 v[jj] = dz;
             }
             prefetch_z1(tg, sg_other);              // next tile of the OTHER pipeline, in front of the one exposed MMA wait
-            if (L::NZ == 1 && t >= 1) tc::mbar_wait(bar_wgd + (1 - p), 1);       // G4(t - 1) has released the shared dz buffer
+            if (L::NZ == 1 && t >= 1) wait_bar(bar_wgd + (1 - p), 1);       // G4(t - 1) has released the shared dz buffer
             unsigned char* Z = ZB + (L::NZ == 2 ? p : 0) * L::ABUF;
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -525,7 +530,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
                     gb2 += v[j];
                 }
             }
-            tc::mbar_wait(bar_wgd + p, 0);               // dz3^T / x2^T were still being read by the TW3 MMAs until here
+            wait_bar(bar_wgd + p, 0);                    // dz3^T / x2^T were still being read by the TW3 MMAs until here
             unsigned char* Z = ZB + (L::NZ == 2 ? p : 0) * L::ABUF;
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -596,7 +601,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
                 }
             }
             if (has_x) {                                             // st holds z1 of tile t2 (prefetch_z1)
-                if (has_t) tc::mbar_wait(bar_wgd + p, 1);            // TW2 += dz2^T x1 of tile t still reads the x buffer
+                if (has_t) wait_bar(bar_wgd + p, 1);                 // TW2 += dz2^T x1 of tile t still reads the x buffer
                 put_x1(XB + p * L::ABUF, st, Pipe<0>{});
                 arrive(p);
             }
@@ -620,8 +625,8 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
             STAMP_E(kq, 24);
         }
         // every MMA of this CTA has completed before TW2 / TW3 are read
-        if (T > 0) tc::mbar_wait(bar_wgd + 0, 1);
-        if (T > 1) tc::mbar_wait(bar_wgd + 1, 1);
+        if (T > 0) wait_bar(bar_wgd + 0, 1);
+        if (T > 1) wait_bar(bar_wgd + 1, 1);
         tc::fence_after_sync();
         // ---- per-CTA partials: weight gradients from TMEM
         float* my = partial + (int64_t)blockIdx.x * EDGE_PARTIAL;
