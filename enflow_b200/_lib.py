@@ -31,7 +31,7 @@ SIGNATURES = {
     'enflow_timing_enable': (i32, [i32]),
     'enflow_timing_kinds': (i32, []),
     'enflow_timing_read': (i32, [C.POINTER(f32), C.POINTER(i32)]),
-    'enflow_adam_step': (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]),
+    'enflow_adam_step': (i32, [vp, vp, vp, vp, i64, vp, f32, vp, f32, f32, f32, vp]),
     'enflow_param_layout': (i64, [i32, i32, C.POINTER(i64), C.POINTER(i64)]),
     'enflow_lj_prior_workspace_doubles': (i64, [i32]),
     'enflow_lj_prior_forces': (i32, [vp, i32, box3, f64, f64, vp, vp, vp, vp]),

@@ -101,8 +101,8 @@ int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts) {
 }
 
 int enflow_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int* step,
-                     float lr, float beta1, float beta2, float eps, void* stream) {
-    return enf_adam_step(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, ST(stream));
+                     float lr, const float* lr_dev, float beta1, float beta2, float eps, void* stream) {
+    return enf_adam_step(params, grads, exp_avg, exp_avg_sq, n, step, lr, lr_dev, beta1, beta2, eps, ST(stream));
 }
 
 int64_t enflow_lj_prior_workspace_doubles(int N) { return enf_lj_prior_workspace_doubles(N); }

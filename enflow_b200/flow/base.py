@@ -36,7 +36,7 @@ class BaseFlow(torch.nn.Module):
 
     def _flatten(self):
         params = self._ordered_params()
-        if not params or not hasattr(self.dequantize, 'PARAM_ORDER'):
+        if not params:
             return
         nf, L = self.networks[0].input_nf, len(self.networks)
         total, offs, cnts = _lib.param_layout(nf, L)
@@ -53,7 +53,8 @@ class BaseFlow(torch.nn.Module):
         for i, net in enumerate(self.networks):
             end = offs[15 * (i + 1)] if 15 * (i + 1) < len(offs) else total
             net._flat_view = flat[offs[15 * i]:end]
-        self.dequantize._flat_view = flat[offs[15 * L]:]
+        if hasattr(self.dequantize, 'PARAM_ORDER'):        # ArgMax: its slice of the flat buffer; others keep their own parameters
+            self.dequantize._flat_view = flat[offs[15 * L]:]
 
     def _apply(self, fn, recurse=True):
         super()._apply(fn, recurse)

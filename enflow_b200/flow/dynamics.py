@@ -35,6 +35,7 @@ class _FlowFn(torch.autograd.Function):
                          float(flow.networks[0].coords_weight), _lib.MODES[flow.precision])
         nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), int(training))
         ws = flow._take_workspace(nbytes, dev, training)
+        flow._last_ws = ws
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         ho, go, po, vo = new(b['N'], nf), new(b['N'], nf), new(b['N'], 3), new(b['N'], 3)
         ldj_mol, ldj = new(b['B']), new(1)
@@ -69,6 +70,8 @@ class _FlowFn(torch.autograd.Function):
                                           p(b['box']), p(b['off']), p(ctx.eps), p(ctx.ws), ctx.nbytes, p(dh), p(dg),
                                           p(dpos), p(dvel), p(dldj), p(ctx.status), _lib.stream()))
         flow._release_workspace(ctx.ws)
+        if flow.check_status and int(ctx.status.item()) & 4:
+            raise RuntimeError('enflow_b200: k_edge_bwd_tc needs its shared-memory window 1 KB aligned')
         if flow._dp_group is not None and not flow._dp_defer:   # data parallel: one all-reduce over the flat buffer
             from ..parallel import allreduce_mean_
             allreduce_mean_(grads, flow._dp_group)
@@ -82,6 +85,7 @@ class LFIntegrator(BaseFlow):
         self._edge_caps = {}
         self._ws_cache = None
         self._ws_busy = False
+        self._last_ws = None
         self._dp_group = None
         self._dp_defer = False      # True: the caller all-reduces flat_grads itself (GraphedTrainStep)
         self.check_status = True
@@ -120,8 +124,10 @@ class LFIntegrator(BaseFlow):
             self._edge_caps[key] = cap
         return cap
 
-    def _run(self, data, eps, training):
+    def _run(self, data, eps, training, h_graph=None):
         b = _prep(data)
+        if h_graph is not None:              # keep h attached to autograd (dequantiser with parameters upstream)
+            b['h'] = h_graph.to(torch.float32).contiguous()
         cap = self._capacity(data, b)
         if eps is not None:
             eps = _lib.f32c(eps.to(b['dev']))
@@ -138,8 +144,8 @@ class LFIntegrator(BaseFlow):
                                  '(the reference raises IndexError at enflow/data/base.py:137)')
             if not (code & 1):
                 break
-            self._release_workspace(self._ws_cache)
-            cap *= 2
+            self._release_workspace(self._last_ws)       # only the buffer THIS call was handed (a pending backward of an
+            cap *= 2                                     # earlier forward may own the cached one)
             self._edge_caps[(b['B'], b['N'])] = cap
         return out
 
@@ -147,14 +153,27 @@ class LFIntegrator(BaseFlow):
         """`dynamics.py:10-23`. ``eps`` (optional) injects the ArgMax noise; default ``torch.randn``.
         ``dequantize=False`` skips the ArgMax step (h is used as given): the exact inverse of
         ``reverse(..., quantize=False)``."""
+        from ..nn.argmax import ArgMax
+        log_q = None
         if not dequantize:
             eps = None
-        elif eps is None:
-            eps = torch.randn(data.h.size(), device=data.h.device)          # argmax.py:17
-        training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        h, g, pos, vel, ldj, ldj_mol, _ = self._run(data, eps, training)
+        elif isinstance(self.dequantize, ArgMax):            # fused into the C call (K4), noise injected
+            if eps is None:
+                eps = torch.randn(data.h.size(), device=data.h.device)          # argmax.py:17
+        else:
+            # any other dequantiser (nn/floor.py, user modules): `data.h, ldj = self.dequantize(data.h)` as dynamics.py:11
+            # does, on the host side with autograd; the coupling stack then starts from that h
+            if eps is not None:
+                raise ValueError('eps injects the ArgMax noise; this flow was built with '
+                                 f'{type(self.dequantize).__name__}')
+            data.h, log_q = self.dequantize(data.h)
+        training = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or data.h.requires_grad)
+        h_in = data.h
+        h, g, pos, vel, ldj, ldj_mol, _ = self._run(data, eps, training, h_in if h_in.requires_grad else None)
         data.h, data.g, data.pos, data.vel = h, g, pos, vel
         data.ldj_mol = ldj_mol
+        if log_q is not None:
+            ldj = ldj + log_q
         return data, ldj
 
     @torch.no_grad()
@@ -167,6 +186,8 @@ class LFIntegrator(BaseFlow):
         nf = self.networks[0].input_nf
         h, g, pos, vel = (b[k].clone() for k in ('h', 'g', 'pos', 'vel'))
         p = _lib.ptr
+        from ..nn.argmax import ArgMax
+        fused_q = isinstance(self.dequantize, ArgMax)        # one_hot(argmax) inside the C call; others on the host below
         while True:
             dims = _lib.Dims(b['B'], b['N'], nf, len(self.networks), cap, b['max_n'], float(self.dt),
                              float(self.networks[0].coords_weight), _lib.MODES[self.precision])
@@ -175,7 +196,7 @@ class LFIntegrator(BaseFlow):
             neg = torch.empty(b['B'], dtype=torch.float32, device=dev)
             status = torch.zeros(1, dtype=torch.int32, device=dev)
             _lib.check(L.enflow_flow_reverse(ctypes.byref(dims), p(self.flat_params), p(h), p(g), p(pos), p(vel),
-                                             p(b['box']), p(b['r_cut']), p(b['off']), p(ws), nbytes, int(quantize),
+                                             p(b['box']), p(b['r_cut']), p(b['off']), p(ws), nbytes, int(quantize and fused_q),
                                              p(neg), p(status), _lib.stream()))
             code = int(status.item()) if self.check_status else 0
             if code & 2:
@@ -185,6 +206,8 @@ class LFIntegrator(BaseFlow):
             cap *= 2
             self._edge_caps[(b['B'], b['N'])] = cap
             h, g, pos, vel = (b[k].clone() for k in ('h', 'g', 'pos', 'vel'))
+        if quantize and not fused_q:
+            h = self.dequantize.reverse(h)                   # dynamics.py:35
         data.h, data.g, data.pos, data.vel = h, g, pos, vel
         data.neg_ldj_mol = neg
         return data

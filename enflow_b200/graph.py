@@ -10,19 +10,32 @@ of kernels per step against ~3.8 ms of launch/Python time when issued eagerly).
 
 Constraints: every batch must have the example's layout (same number of molecules and atoms per molecule; the
 dims of the C calls are baked into the graph); the optimizer must support capture (``torch.optim.Adam(...,
-capturable=True)``); the edge capacity is fixed at capture time and overflow is reported by ``step.status``
-(device flag, checked on demand) instead of the eager path's automatic retry.
+capturable=True)`` or ``FlatAdam``); the edge capacity is fixed at capture time: with ``check_overflow=True`` the step
+is two graphs (gradients; optimizer) and the device flag is read between them, so an overflowing batch raises
+``EdgeCapacityOverflow`` BEFORE the optimizer runs (``Main`` recaptures with twice the capacity and redoes the step);
+otherwise ``step.overflowed()`` reports it on demand.  With ``FlatAdam`` the learning rate lives on the device, so a
+scheduler stepped between replays (the reference's per-batch StepLR) is followed.
 """
 import torch
 
 from .data.base import Data
 
 
+class EdgeCapacityOverflow(RuntimeError):
+    """The replayed step met more edges than the capacity captured in the graph (gradients are from a truncated list;
+    the optimizer has not run).  Recapture with a larger capacity (``model._edge_caps``) and redo the step."""
+
+
 class GraphedTrainStep:
-    def __init__(self, model, nll, optimizer, example, warmup=3, eps=None):
+    def __init__(self, model, nll, optimizer, example, warmup=3, eps=None, scheduler=None, check_overflow=False):
         if not example.pos.is_cuda:
             raise RuntimeError('GraphedTrainStep needs the example batch on the CUDA device')
         self.model, self.nll, self.optimizer = model, nll, optimizer
+        # A scheduler changes param_groups[0]['lr'] between replays: only an optimizer that keeps the learning rate on
+        # the device (FlatAdam.sync_lr) can follow it inside a captured graph
+        if scheduler is not None and not hasattr(optimizer, 'sync_lr'):
+            raise ValueError('GraphedTrainStep with a scheduler needs enflow_b200.optim.FlatAdam (device-resident lr)')
+        self.check_overflow = bool(check_overflow)
         # optional static ArgMax-noise buffer (refill it before a replay); default: torch.randn inside the graph
         self.eps = None if eps is None else eps.detach().to(example.pos.device, torch.float32).contiguous().clone()
         f32 = lambda t: t.detach().to(torch.float32).contiguous().clone()
@@ -51,8 +64,9 @@ class GraphedTrainStep:
         # Data parallel: the NCCL all-reduce is NOT captured.  Two graphs (everything up to the gradients; the
         # optimizer) with one eager all-reduce of the flat gradient buffer between their replays.
         self.dp = getattr(model, '_dp_group', None) is not None
+        self.split = self.dp or self.check_overflow      # gradients and optimizer as two graphs
         self.graph = torch.cuda.CUDAGraph()
-        if self.dp:
+        if self.split:
             model._dp_defer = True
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
@@ -97,10 +111,15 @@ class GraphedTrainStep:
     def __call__(self, batch=None):
         if batch is not None:
             self.load(batch)
+        if hasattr(self.optimizer, 'sync_lr'):
+            self.optimizer.sync_lr()                    # outside the graph: the captured kernel reads the device scalar
         self.graph.replay()
-        if self.dp:
-            from .parallel import allreduce_mean_
-            allreduce_mean_(self.model.flat_grads, self.model._dp_group)
+        if self.split:
+            if self.check_overflow and self.overflowed():
+                raise EdgeCapacityOverflow('edge capacity captured in the CUDA graph exceeded by this batch')
+            if self.dp:
+                from .parallel import allreduce_mean_
+                allreduce_mean_(self.model.flat_grads, self.model._dp_group)
             self.graph_opt.replay()
         return self.loss
 

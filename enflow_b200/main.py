@@ -151,16 +151,23 @@ class Main:
     def _graphed_step(self, data):
         """One optimizer step through `GraphedTrainStep`; None when this batch does not have the captured layout
         (e.g. the last, shorter batch of an epoch), in which case the caller launches the step eagerly."""
-        from .graph import GraphedTrainStep
+        from .graph import EdgeCapacityOverflow, GraphedTrainStep
         n_cpu = data.meta()[3]
         g = getattr(self, '_gstep', None)
         if g is None:
             # the capture's warm-up IS this batch's step (one eager step), the capture itself executes nothing
-            self._gstep = GraphedTrainStep(self.model, self.nll, self.optimizer, data, warmup=1)
+            self._gstep = GraphedTrainStep(self.model, self.nll, self.optimizer, data, warmup=1, scheduler=self.scheduler,
+                                           check_overflow=True)
             return self._gstep.warmup_loss
         if not torch.equal(n_cpu, g._n_cpu):
             return None
-        return g(data)
+        try:
+            return g(data)
+        except EdgeCapacityOverflow:
+            # more edges than the captured capacity (radius graphs): the optimizer has not run.  Launch this step eagerly
+            # (its own retry doubles model._edge_caps) and capture again at the next batch with the larger capacity.
+            self._gstep = None
+            return None
 
     def train(self):
         if self.world_rank == 0:
@@ -174,15 +181,15 @@ class Main:
             start_time = time.time()
             for i, data in enumerate(self.train_loader):
                 data = data.to(self.local_rank)
-                loss = self._graphed_step(data) if (self.cuda_graph and self.scheduler is None) else None
+                loss = self._graphed_step(data) if self.cuda_graph else None
                 if loss is None:
                     self.optimizer.zero_grad()
                     out, ldj = self.model(data)
                     loss = self.nll(out, ldj)
                     loss.backward()
                     self.optimizer.step()
-                    if self.scheduler:
-                        self.scheduler.step()                    # per batch (main.py:223, Q15)
+                if self.scheduler:
+                    self.scheduler.step()                        # per batch (main.py:223, Q15)
                 losses.append(loss.detach().clone())
             epoch_loss = torch.stack(losses).mean()
             if self.ddp:

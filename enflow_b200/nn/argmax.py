@@ -29,9 +29,17 @@ class ArgMax(nn.Module):
             flat[o - base:o - base + c] = sd[name].detach().to(device, torch.float32).reshape(-1)
         return flat
 
-    @torch.no_grad()
     def forward(self, h, eps=None, mol_off=None):
-        """Returns (z, log_q). ``eps`` defaults to ``torch.randn(h.size())`` like `argmax.py:17`."""
+        """Returns (z, log_q). ``eps`` defaults to ``torch.randn(h.size())`` like `argmax.py:17`.  Stand-alone
+        INFERENCE entry point (no autograd; inside LFIntegrator the dequantiser is part of the fused, differentiable
+        C call): inputs that require a gradient raise instead of silently losing it."""
+        if torch.is_grad_enabled() and h.requires_grad:
+            raise RuntimeError('enflow_b200.ArgMax.forward does not record autograd: differentiate through LFIntegrator '
+                               '(or call it under torch.no_grad() / on detached inputs)')
+        with torch.no_grad():
+            return self._forward(h, eps, mol_off)
+
+    def _forward(self, h, eps=None, mol_off=None):
         L = _lib.lib()
         _lib.require_cuda(h)
         dev = h.device

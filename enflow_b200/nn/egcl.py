@@ -1,8 +1,9 @@
 """EGCL with the reference's constructor, parameter names and forward signature
 (`enflow/nn/egcl.py:5-93`), evaluated by the CUDA kernels of csrc/.
 
-``forward(h, edges) -> (Q [N,1], F [N,3], G [N,nf])`` is the stand-alone (inference) entry point;
-training runs through ``LFIntegrator`` whose fused C call handles all layers and the backward pass.
+``forward(h, edges) -> (Q [N,1], F [N,3], G [N,nf])`` is the stand-alone INFERENCE entry point: its outputs do not carry
+autograd (training runs through ``LFIntegrator``, whose fused C calls hold the hand-written backward of every layer).
+Called with autograd enabled on inputs that require a gradient it raises instead of silently dropping that gradient.
 """
 import torch
 from torch import nn
@@ -50,12 +51,19 @@ class EGCL(nn.Module):
             flat[o:o + c] = sd[name].detach().to(device, torch.float32).reshape(-1)
         return flat
 
-    @torch.no_grad()
     def forward(self, h, edges):
+        self._grad_mode = torch.is_grad_enabled()
+        with torch.no_grad():
+            return self._forward(h, edges)
+
+    def _forward(self, h, edges):
         L = _lib.lib()
         if self.hidden_nf != L.enflow_hidden():
             raise ValueError(f'kernels are built for hidden_nf={L.enflow_hidden()}')
         _lib.require_cuda(h, edges.coord)
+        if self._grad_mode and (h.requires_grad or edges.coord.requires_grad):
+            raise RuntimeError('enflow_b200.EGCL.forward does not record autograd: differentiate through LFIntegrator '
+                               '(or call it under torch.no_grad() / on detached inputs)')
         if edges.csr is None:
             raise ValueError('EGCL.forward needs Edges built by Data.edges on the GPU (row-grouped CSR attached)')
         dev = h.device

@@ -15,11 +15,38 @@ class FlatAdam(torch.optim.Optimizer):
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         self.model = model
         params = model._ordered_params()
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        # torch.optim.Adam's full set of group defaults: a state_dict written here loads into torch.optim.Adam (the
+        # reference, main.py:177,203) and steps there (Adam.step reads every one of these keys)
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
+        super().__init__(params, defaults)
         flat = model.flat_params
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=flat.device)
+        # the kernel reads the learning rate from this device scalar, so a captured CUDA graph follows a scheduler:
+        # sync_lr() (outside the graph) refreshes it whenever param_groups[0]['lr'] changed
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=flat.device)
+        self._lr_seen = float(lr)
+
+    def sync_lr(self):
+        lr = float(self.param_groups[0]['lr'])
+        if lr != self._lr_seen:
+            self.lr_dev.fill_(lr)
+            self._lr_seen = lr
+
+    def _gather_foreign_grads(self):
+        """Gradients normally ARE views of model.flat_grads (the fused backward wrote them there).  A .grad that is
+        its own tensor (accumulated by autograd into a clone, clipped into a fresh tensor, set by user code) is copied
+        into its slice so the kernel never applies stale values."""
+        m = self.model
+        offs, cnts = m._layout
+        base, esz = m.flat_grads.data_ptr(), m.flat_grads.element_size()
+        for p, o, c in zip(self.param_groups[0]['params'], offs, cnts):
+            if p.grad is None:
+                raise RuntimeError('FlatAdam.step() needs gradients from the fused backward pass on every parameter')
+            if p.grad.data_ptr() != base + o * esz or p.grad.dtype != m.flat_grads.dtype:
+                m.flat_grads[o:o + c].copy_(p.grad.reshape(-1))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -28,14 +55,14 @@ class FlatAdam(torch.optim.Optimizer):
         if m.flat_params.device != self.exp_avg.device:
             raise RuntimeError('FlatAdam: the model moved to another device after the optimizer was built')
         grp = self.param_groups[0]
-        # every parameter gradient is a view of model.flat_grads (the backward pass wrote them there)
-        if any(p.grad is None for p in grp['params']):
-            raise RuntimeError('FlatAdam.step() needs gradients from the fused backward pass on every parameter')
+        self._gather_foreign_grads()
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         _lib.require_cuda(m.flat_params)
         _lib.check(_lib.lib().enflow_adam_step(_lib.ptr(m.flat_params), _lib.ptr(m.flat_grads), _lib.ptr(self.exp_avg),
                                                _lib.ptr(self.exp_avg_sq), m.flat_params.numel(), _lib.ptr(self.step_dev),
-                                               float(grp['lr']), float(grp['betas'][0]), float(grp['betas'][1]),
-                                               float(grp['eps']), _lib.stream()))
+                                               float(grp['lr']), _lib.ptr(self.lr_dev), float(grp['betas'][0]),
+                                               float(grp['betas'][1]), float(grp['eps']), _lib.stream()))
         return loss
 
     # ---- torch.optim.Adam-compatible (de)serialisation ------------------------------------------------------
@@ -62,3 +89,4 @@ class FlatAdam(torch.optim.Optimizer):
         for k, v in sd['param_groups'][0].items():
             if k != 'params':
                 self.param_groups[0][k] = v
+        self.sync_lr()

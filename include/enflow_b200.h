@@ -65,9 +65,10 @@ int enflow_timing_read(float* ms, int* counts);
 int64_t enflow_param_layout(int nf, int L, int64_t* offsets, int64_t* counts);
 
 /* ---- optimizer step on the flat buffers (torch.optim.Adam in enflow/main.py:177,222): in-place Adam over n floats,
- * step counter on the device (int[1], incremented by the call) so the launch is CUDA-graph capturable. */
+ * step counter on the device (int[1], incremented by the call) so the launch is CUDA-graph capturable.  lr_dev
+ * (nullable device float[1]) overrides lr: a captured graph then follows a per-batch StepLR (main.py:188,223). */
 int enflow_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t* step,
-                     float lr, float beta1, float beta2, float eps, void* stream);
+                     float lr, const float* lr_dev, float beta1, float beta2, float eps, void* stream);
 
 /* ---- K0 neighbour list: Data.edges (enflow/data/base.py:122-144, utils/helpers.py:15-29) -------
  * pos/box are fp32 (pos_is_f64 = 0) or fp64 (1).  Output is grouped by row (CSR): row/col [E_cap],

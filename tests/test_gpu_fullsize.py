@@ -103,3 +103,65 @@ def test_mid_size_train_step_vs_oracle(B):
     worst = max(np.linalg.norm(to_np(p.grad) - ref_grads[k].numpy()) / max(np.linalg.norm(ref_grads[k].numpy()), 1e-300)
                 for k, p in model.named_parameters())
     assert worst < 1e-4, worst
+
+
+# ---- the other BASELINE.json configurations at bench size: sub-batch vs oracle + independence of molecules --------
+def _model_for(nf, precision, seed=0):
+    from enflow_b200.data import synthetic as syn
+    from gpu_util import build_model
+    return build_model(syn.make_weights(nf, 128, L, seed=seed, coord_gain=0.5), nf, L, precision=precision), \
+        syn.make_weights(nf, 128, L, seed=seed, coord_gain=0.5)
+
+
+def _sub_batch_and_independence(config, B, nf, precision, tol, lo, hi, kw=None, reverse=False):
+    """Run the full-size batch once; molecules [lo, hi) processed alone must give the same per-molecule results
+    (they never interact: data/base.py:129-142, loss.py:13), and that sub-batch must match the fp64 oracle."""
+    from enflow_b200.data import synthetic as syn
+    arrs = syn.make_batch(config, B, **(kw or {}))
+    eps = syn.make_noise(int(arrs['N'].sum()), nf)
+    model, sd = _model_for(nf, precision)
+    sub, sl = _take(arrs, lo, hi)
+    p = orc.params_to_torch(sd)
+    if not reverse:
+        with torch.no_grad():
+            big, _ = model(gpu_batch(arrs), eps=torch.as_tensor(eps))
+            small, _ = model(gpu_batch(sub), eps=torch.as_tensor(eps[sl]))
+        for k in ('pos', 'vel', 'h', 'g'):
+            assert rel_err(to_np(getattr(small, k)), to_np(getattr(big, k)[sl])) < max(2e-6, tol / 5), k
+        assert rel_err(to_np(small.ldj_mol), to_np(big.ldj_mol[lo:hi])) < max(2e-6, tol / 5)
+        ref, _, ref_ldj_mol = orc.lf_forward(p, L, orc.to_torch(sub), syn.TRAIN_DT, torch.as_tensor(eps[sl], dtype=torch.float64))
+        for k in ('pos', 'vel', 'h', 'g'):
+            assert rel_err(to_np(getattr(small, k)), ref[k].numpy()) < tol, k
+        assert rel_err(to_np(small.ldj_mol), ref_ldj_mol.numpy()) < tol
+    else:
+        with torch.no_grad():
+            big = model.reverse(gpu_batch(arrs), quantize=False)
+            small = model.reverse(gpu_batch(sub), quantize=False)
+        for k in ('pos', 'vel', 'h', 'g'):
+            assert rel_err(to_np(getattr(small, k)), to_np(getattr(big, k)[sl])) < max(2e-6, tol / 5), k
+        assert rel_err(to_np(small.neg_ldj_mol), to_np(big.neg_ldj_mol[lo:hi])) < max(2e-6, tol / 5)
+        ref, ref_neg = orc.lf_reverse(p, L, orc.to_torch(sub), syn.TRAIN_DT, quantize=False)
+        for k in ('pos', 'vel', 'h', 'g'):
+            assert rel_err(to_np(getattr(small, k)), ref[k].numpy()) < 2 * tol, k
+        assert rel_err(to_np(small.neg_ldj_mol), ref_neg.numpy()) < 2 * tol
+
+
+def test_full_size_c1_train_yaml_shape():
+    """C1: example/train.yaml shape, 64 x 22 atoms, radius graph in the PBC-quirk regime, fp32-accurate mode."""
+    _sub_batch_and_independence('c1', 64, 4, 'fp32_tc', 1e-5, 20, 28)
+
+
+def test_full_size_c3_lj55():
+    """C3: 1024 LJ-55 clusters, fully connected, one feature."""
+    _sub_batch_and_independence('c3', 1024, 1, 'fp32_tc', 1e-5, 500, 504)
+
+
+def test_full_size_c5_bf16_radius_graph():
+    """C5: 32 x 500-atom fragments, radius-cutoff graph, bf16 edge MLP (tolerance 1e-2)."""
+    _sub_batch_and_independence('c5', 32, 5, 'bf16', 1e-2, 7, 8, kw={'n_atoms': 500})
+
+
+def test_full_size_c4_inverse_pass():
+    """C4: the generate.yaml inverse pass on 16 384 x 22-atom latents (PBC regime), product mode, against the oracle's
+    inverse on a sub-batch, with the per-molecule -sum(Q)."""
+    _sub_batch_and_independence('c4', 16384, 4, 'fp32_tc', 1e-5, 9000, 9008, reverse=True)
