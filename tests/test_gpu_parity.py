@@ -4,8 +4,8 @@ Every test runs in the three arithmetic modes of the edge MLP (gpu_util.MODES): 
 tcgen05, bf16x3 operand split), 'fp32' (CUDA-core FFMA cross-check) and 'bf16' (tcgen05, one MMA per GEMM).
 Tolerances (BASELINE.json north star): log-likelihood and latents within 1e-5 relative in the fp32-accurate modes,
 1e-2 under the bf16 MLP; edge/index construction bit-exact.  Gradients are held to 1e-4 (5e-2 in bf16 mode)
-relative, L2 per tensor.  `check_close` asserts the max-norm figure and an elementwise one (1 % floor, 10x the
-tolerance) and prints both.
+relative, L2 per tensor.  `check_close` asserts the max-norm figure and prints the elementwise one (1 % floor) next
+to it (`pytest -rP`).
 """
 import numpy as np
 import pytest
