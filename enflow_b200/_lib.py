@@ -19,7 +19,7 @@ f64, u64, box3 = C.c_double, C.c_uint64, C.POINTER(C.c_double)
 class Dims(C.Structure):
     """enflow_dims_t"""
     _fields_ = [('B', i32), ('N', i32), ('nf', i32), ('L', i32), ('E_cap', i32), ('max_n', i32),
-                ('dt', f32), ('coords_weight', f32), ('mode', i32)]
+                ('dt', f32), ('coords_weight', f32), ('mode', i32), ('fc', i32)]
 
 
 # name -> (restype, argtypes); mirrors include/enflow_b200.h one to one
@@ -40,6 +40,8 @@ SIGNATURES = {
     'enflow_lj_prior_run': (i32, [vp, vp, i32, box3, f64, f64, f64, f64, f64, i32, u64, u64, vp, vp, vp]),
     'enflow_edges_workspace_ints': (i64, [i32]),
     'enflow_build_edges': (i32, [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'enflow_fc_check': (i32, [vp, vp, vp, vp, i32, vp, vp]),
+    'enflow_fc_build': (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'enflow_build_col_perm': (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     'enflow_segment_sum128': (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
     'enflow_segment_sum3': (i32, [vp, vp, vp, i32, i32, i32, f32, i32, vp, vp]),

@@ -141,6 +141,14 @@ int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const f
                                     rowptr, ref_pos, E_dev, status, ws, ST(stream));
 }
 
+int enflow_fc_check(const float* pos, const float* box, const float* r_cut, const int* mol_off, int B, int* status,
+                    void* stream) {
+    return enf_fc_check(pos, box, r_cut, mol_off, B, status, ST(stream));
+}
+int enflow_fc_build(const int* mol_off, int B, int N, int E_cap, int* row, int* col, int* rowptr, int* E_dev,
+                    int* colptr, int* perm, int* eoff, int* status, void* stream) {
+    return enf_fc_build(mol_off, B, N, E_cap, row, col, rowptr, E_dev, colptr, perm, eoff, status, ST(stream));
+}
 int enflow_build_col_perm(const int* col, const int* rowptr, const int* mol_off, int B, int N, int E_cap,
                           const int* E_dev, int* colptr, int* perm, int* ws, void* stream) {
     return enf_build_col_perm(col, rowptr, mol_off, B, N, E_cap, E_dev, colptr, perm, ws, nullptr, ST(stream));

@@ -8,6 +8,7 @@ struct enflow_dims_t {
     int32_t B, N, nf, L, E_cap, max_n;
     float dt, coords_weight;
     int32_t mode;      // 0 = fp32 on the FFMA pipe, 1 = tcgen05 bf16x3 split (fp32-accurate), 2 = tcgen05 bf16
+    int32_t fc;        // 1 = fully connected regime assumed: implicit all-pairs list built once, re-proved per layer (fc.cu)
 };
 
 #define TIMED(kind, call)        \
@@ -47,6 +48,7 @@ struct Workspace {
     float *F, *G, *trans, *wr, *runs;
     int* run_scratch;
     int* edges_ws;
+    int* fc_eoff;            // per-molecule edge offsets of the implicit all-pairs list (fc mode)
     float* logq_atom;
     double* logq_mol;
     float* log_q;
@@ -80,8 +82,13 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
     }
     for (int l = 0; l < saved_layers; ++l) {
         LayerSave& s = w.layer[l];
-        s.row = b.take<int>(E); s.col = b.take<int>(E); s.rowptr = b.take<int>(N + 1); s.E_dev = b.take<int>(2);
-        s.mis = b.take<int>(N + 2);
+        if (d.fc && l > 0) {          // one neighbour list for every coupling step
+            const LayerSave& s0 = w.layer[0];
+            s.row = s0.row; s.col = s0.col; s.rowptr = s0.rowptr; s.E_dev = s0.E_dev; s.mis = s0.mis;
+        } else {
+            s.row = b.take<int>(E); s.col = b.take<int>(E); s.rowptr = b.take<int>(N + 1); s.E_dev = b.take<int>(2);
+            s.mis = b.take<int>(N + 2);
+        }
         s.Q = b.take<float>(N); s.s = b.take<float>(E);
         s.z2 = d.mode == 0 ? b.take<float>(E * H) : nullptr;
         s.z3 = d.mode == 0 ? b.take<float>(E * H) : nullptr;
@@ -95,6 +102,7 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
     w.runs = d.mode ? b.take<float>((size_t)enf_run_rows(d.E_cap, d.N) * H) : nullptr;
     w.run_scratch = b.take<int>((size_t)enf_scan_scratch_ints(d.N + 2));
     w.edges_ws = b.take<int>((size_t)enf_edges_workspace_ints(d.N));
+    w.fc_eoff = b.take<int>((size_t)d.B + 2);
     w.logq_atom = b.take<float>(N); w.logq_mol = b.take<double>(d.B); w.log_q = b.take<float>(1);
     if (training) {
         w.dQ = b.take<float>(N); w.dF = b.take<float>(N * 3); w.dG = b.take<float>(N * nf);
@@ -114,6 +122,7 @@ int check_dims(const enflow_dims_t* d) {
     ENF_CHECK_ARG(d->L >= 1 && d->L <= 16, "L=%d outside [1,16]", d->L);
     ENF_CHECK_ARG(d->B >= 0 && d->N >= 0 && d->E_cap >= 0, "negative size");
     ENF_CHECK_ARG(d->mode >= 0 && d->mode <= 2, "mode=%d outside [0,2]", d->mode);
+    ENF_CHECK_ARG(d->fc == 0 || d->fc == 1, "fc=%d is not 0 or 1", d->fc);
     return ENF_OK;
 }
 
@@ -135,8 +144,11 @@ void copy_f(float* dst, const float* src, size_t n, cudaStream_t st) {
 int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv, const float* lp, const float* packed,
                  const unsigned char* tcimg, const float* h, const float* pos, const float* box, const float* r_cut, const int* mol_off,
                  int* status, cudaStream_t st) {
-    TIMED(TK_EDGES, enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
-                                     sv.E_dev, status, w.edges_ws, st));
+    if (d.fc)      // the list exists (fc_lists); prove that these positions are still in the regime where it is the answer
+        TIMED(TK_EDGES, enf_fc_check(pos, box, r_cut, mol_off, d.B, status, st));
+    else
+        TIMED(TK_EDGES, enf_build_edges_t<float>(pos, box, r_cut, mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, nullptr,
+                                         sv.E_dev, status, w.edges_ws, st));
     TIMED(TK_NODE_PRE, enf_node_pre_fwd(h, d.N, d.nf, lp, sv.P, sv.S, sv.Q, st));
     if (d.mode == 0) {
         TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, packed, d.nf, w.wr,
@@ -144,7 +156,7 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
         TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
     } else {
         // tensor-core path: the kernel reduces silu(z2) over each row into per-run partials; no [E,H] store
-        ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
+        if (!d.fc) ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
         TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, tcimg, d.nf,
                                            sv.rowptr, sv.mis, w.runs, sv.s, w.trans, st));
         // agg = row sums of the run partials, F = coords_weight * row means of trans (helpers.py:62-70): one launch
@@ -157,6 +169,15 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
         TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
     else
         TIMED(TK_NODE_POST, enf_node_post_fwd_tc(d.mode, h, sv.agg, d.N, d.nf, lp, tcimg, sv.z4, w.G, st));
+    return ENF_OK;
+}
+
+// fc mode: the all-pairs list, its run index and (training) its column-grouped permutation, once per pass
+int fc_lists(const enflow_dims_t& d, const Workspace& w, const int* mol_off, int training, int* status, cudaStream_t st) {
+    const LayerSave& sv = w.layer[0];
+    TIMED(TK_EDGES, enf_fc_build(mol_off, d.B, d.N, d.E_cap, sv.row, sv.col, sv.rowptr, sv.E_dev, training ? w.colptr : nullptr,
+                                 training ? w.perm : nullptr, w.fc_eoff, status, st));
+    if (d.mode) ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
     return ENF_OK;
 }
 
@@ -203,6 +224,7 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
     copy_f(w.g[0], g_in, N * nf, st);
     copy_f(w.pos[0], pos_in, N * 3, st);
     copy_f(w.vel[0], vel_in, N * 3, st);
+    if (d.fc) ENF_TRY(fc_lists(d, w, mol_off, training, status, st));
     for (int l = 0; l < d.L; ++l) {
         const int cur = training ? l : (l & 1);
         const bool last = l == d.L - 1;
@@ -248,14 +270,16 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         // edge_model + force_model (egcl.py:57-63,71-75); P/S were kept by the forward pass
         // column-grouped view of the edges; reused as is when this layer's list equals the one just processed
         // (fully connected regime: the neighbour list is the same at every coupling step)
-        const int* skip = nullptr;
-        if (l < d.L - 1) {
-            const LayerSave& nx = w.layer[l + 1];
-            ENF_TRY(enf_edges_same(sv.row, sv.col, sv.E_dev, nx.row, nx.col, nx.E_dev, w.same, st));
-            skip = w.same;
+        if (!d.fc) {      // (fc mode: the forward pass left the permutation of the one list in colptr / perm)
+            const int* skip = nullptr;
+            if (l < d.L - 1) {
+                const LayerSave& nx = w.layer[l + 1];
+                ENF_TRY(enf_edges_same(sv.row, sv.col, sv.E_dev, nx.row, nx.col, nx.E_dev, w.same, st));
+                skip = w.same;
+            }
+            TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
+                                                  w.edges_ws, skip, st));
         }
-        TIMED(TK_COL_PERM, enf_build_col_perm(sv.col, sv.rowptr, mol_off, d.B, d.N, d.E_cap, sv.E_dev, w.colptr, w.perm,
-                                              w.edges_ws, skip, st));
         if (d.mode == 0) {
             TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P, sv.S, lp, nf,
                                             w.wr, sv.z2, sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg,
@@ -300,6 +324,7 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
         ENF_TRY(enf_tc_pack_layers(params, nf, d.L, enf_egcl_offsets(nf).size, tc_image(w, 0), enf_tc_pack_bytes(), st));
     }
     const LayerSave& sv = w.layer[0];
+    if (d.fc) ENF_TRY(fc_lists(d, w, mol_off, 0, status, st));
     for (int l = d.L - 1; l >= 0; --l) {
         TIMED(TK_COUPLING, enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,

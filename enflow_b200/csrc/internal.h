@@ -12,6 +12,12 @@ int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, in
 int enf_edges_same(const int* row_a, const int* col_a, const int* E_a, const int* row_b, const int* col_b,
                    const int* E_b, int* same, cudaStream_t st);
 
+// implicit all-pairs lists in the fully connected regime (fc.cu)
+int enf_fc_check(const float* pos, const float* box, const float* r_cut, const int* mol_off, int B, int* status,
+                 cudaStream_t st);
+int enf_fc_build(const int* mol_off, int B, int N, int E_cap, int* row, int* col, int* rowptr, int* E_dev, int* colptr,
+                 int* perm, int* eoff, int* status, cudaStream_t st);
+
 int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
                        cudaStream_t st);
 int enf_segment_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int mean, float scale,

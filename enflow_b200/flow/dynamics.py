@@ -32,7 +32,7 @@ class _FlowFn(torch.autograd.Function):
         dev = b['dev']
         nf = flow.networks[0].input_nf
         dims = _lib.Dims(b['B'], b['N'], nf, len(flow.networks), cap, b['max_n'], float(flow.dt),
-                         float(flow.networks[0].coords_weight), _lib.MODES[flow.precision])
+                         float(flow.networks[0].coords_weight), _lib.MODES[flow.precision], int(flow._fc_now))
         nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), int(training))
         ws = flow._take_workspace(nbytes, dev, training)
         flow._last_ws = ws
@@ -83,6 +83,10 @@ class LFIntegrator(BaseFlow):
     def __init__(self, networks, dequant_network, dt):
         super().__init__(networks, dequant_network, dt)
         self._edge_caps = {}
+        # batch layouts (B, N) whose first neighbour list was exactly all ordered pairs: the C calls then assume the fully
+        # connected regime (list by index arithmetic, proved per layer on the device) and fall back to K0 on status bit 8
+        self._fc_keys = {}
+        self._fc_now = False
         self._ws_cache = None
         self._ws_busy = False
         self._last_ws = None
@@ -122,7 +126,12 @@ class LFIntegrator(BaseFlow):
             cap = e0 if e0 == fc else int(1.25 * e0) + 4096
             cap = max(cap, 128)
             self._edge_caps[key] = cap
+            self._fc_keys[key] = (e0 == fc and fc > 0, fc)
         return cap
+
+    def _fc(self, b, cap):
+        ok, fc = self._fc_keys.get((b['B'], b['N']), (False, 0))
+        return bool(ok and cap == fc)
 
     def _run(self, data, eps, training, h_graph=None):
         b = _prep(data)
@@ -132,6 +141,7 @@ class LFIntegrator(BaseFlow):
         if eps is not None:
             eps = _lib.f32c(eps.to(b['dev']))
         while True:
+            self._fc_now = self._fc(b, cap)
             out = _FlowFn.apply(self, b, eps, cap, training, b['h'], b['g'], b['pos'], b['vel'],
                                 *(self._ordered_params() if training else ()))
             status = out[6]
@@ -139,6 +149,10 @@ class LFIntegrator(BaseFlow):
             if not self.check_status:
                 break
             code = int(status.item())
+            if code & 8:                 # not fully connected after all (a molecule spread out or a box shrank): K0 from now on
+                self._release_workspace(self._last_ws)
+                self._fc_keys[(b['B'], b['N'])] = (False, 0)
+                continue
             if code & 2:
                 raise IndexError('neighbour list: fewer surviving image points than atoms '
                                  '(the reference raises IndexError at enflow/data/base.py:137)')
@@ -189,8 +203,9 @@ class LFIntegrator(BaseFlow):
         from ..nn.argmax import ArgMax
         fused_q = isinstance(self.dequantize, ArgMax)        # one_hot(argmax) inside the C call; others on the host below
         while True:
+            fc = self._fc(b, cap)
             dims = _lib.Dims(b['B'], b['N'], nf, len(self.networks), cap, b['max_n'], float(self.dt),
-                             float(self.networks[0].coords_weight), _lib.MODES[self.precision])
+                             float(self.networks[0].coords_weight), _lib.MODES[self.precision], int(fc))
             nbytes = L.enflow_flow_workspace_bytes(ctypes.byref(dims), 0)
             ws = self._take_workspace(nbytes, dev, False)
             neg = torch.empty(b['B'], dtype=torch.float32, device=dev)
@@ -199,6 +214,10 @@ class LFIntegrator(BaseFlow):
                                              p(b['box']), p(b['r_cut']), p(b['off']), p(ws), nbytes, int(quantize and fused_q),
                                              p(neg), p(status), _lib.stream()))
             code = int(status.item()) if self.check_status else 0
+            if code & 8:
+                self._fc_keys[(b['B'], b['N'])] = (False, 0)
+                h, g, pos, vel = (b[k].clone() for k in ('h', 'g', 'pos', 'vel'))
+                continue
             if code & 2:
                 raise IndexError('neighbour list: fewer surviving image points than atoms')
             if not (code & 1):

@@ -124,5 +124,6 @@ class GraphedTrainStep:
         return self.loss
 
     def overflowed(self):
-        """True if the captured edge capacity was exceeded in the last replay (synchronises)."""
-        return bool(int(self.status.item()) & 1)
+        """True if the captured edge capacity was exceeded in the last replay, or the fully connected regime the capture
+        assumed no longer holds (status bits 1 and 8; synchronises)."""
+        return bool(int(self.status.item()) & 9)

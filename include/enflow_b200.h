@@ -11,7 +11,9 @@
  *   - `stream` is a cudaStream_t passed as void*;
  *   - return value 0 = ok; non-zero = failure, message from enflow_last_error() (thread-local);
  *   - `status` (int[1], device) receives OR-ed flags: 1 = edge capacity exceeded (E > E_cap),
- *     2 = the reference's id_mapping lookup would have raised IndexError (data/base.py:137);
+ *     2 = the reference's id_mapping lookup would have raised IndexError (data/base.py:137),
+ *     4 = a tensor-core kernel found its shared-memory window misaligned (nothing was computed),
+ *     8 = dims.fc was set but some molecule is not provably in the fully connected regime (repeat with fc = 0);
  *   - molecules are contiguous: molecule m owns atoms [mol_off[m], mol_off[m+1]).
  *   - hidden width is fixed at 128 (example/train.yaml:19), node features nf <= 8.
  */
@@ -35,6 +37,10 @@ typedef struct {
     float dt;              /* leap-frog step in LJ time units                          */
     float coords_weight;   /* EGCL coords_weight (egcl.py:11), 1.0 in Main             */
     int32_t mode;          /* edge-MLP arithmetic: 0 = fp32 FFMA, 1 = tcgen05 bf16x3 split (fp32-accurate), 2 = tcgen05 bf16 */
+    int32_t fc;            /* 1: the caller expects every molecule to be in the fully connected regime (Data.edges = all ordered
+                              pairs, base.py:122-144 with box >> extent, r_cut >= extent): the list is built once by index
+                              arithmetic and every coupling step only proves the regime on its positions; E_cap must be
+                              sum n(n-1).  A molecule outside the regime sets status bit 8: repeat the pass with fc = 0. */
 } enflow_dims_t;
 
 const char* enflow_last_error(void);
@@ -79,6 +85,15 @@ int enflow_build_edges(const void* pos, const void* box, int pos_is_f64, const f
                        int B, int N, int E_cap, int32_t* row, int32_t* col, int32_t* rowptr, int32_t* ref_pos,
                        int32_t* E_dev, int32_t* status, int32_t* ws, void* stream);
 /* column-grouped view of the same edges (needed by the backward scatter onto `col`): colptr [N+1], perm [E_cap] */
+/* ---- fully connected regime (same reference semantics, base.py:122-144): when box >> extent and r_cut >= extent the
+ * list is all ordered pairs per molecule, row-major.  enflow_fc_check proves that on the given fp32 positions (status
+ * bit 8 if some molecule is not provably in the regime: conditions in csrc/fc.cu); enflow_fc_build writes the list by
+ * index arithmetic: row/col [E_cap], rowptr [N+1], E_dev[2] as K0, optional column-grouped view colptr [N+1] / perm
+ * [E_cap] as enflow_build_col_perm; eoff: B + 2 ints of scratch. */
+int enflow_fc_check(const float* pos, const float* box, const float* r_cut, const int32_t* mol_off, int B, int32_t* status,
+                    void* stream);
+int enflow_fc_build(const int32_t* mol_off, int B, int N, int E_cap, int32_t* row, int32_t* col, int32_t* rowptr,
+                    int32_t* E_dev, int32_t* colptr, int32_t* perm, int32_t* eoff, int32_t* status, void* stream);
 int enflow_build_col_perm(const int32_t* col, const int32_t* rowptr, const int32_t* mol_off, int B, int N, int E_cap,
                           const int32_t* E_dev, int32_t* colptr, int32_t* perm, int32_t* ws, void* stream);
 

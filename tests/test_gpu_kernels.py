@@ -113,7 +113,7 @@ def test_coupling_forward_inverse_and_backward():
 
 def test_c_abi_error_path():
     L = _lib.lib()
-    dims = _lib.Dims(1, 1, 99, 1, 1, 1, 0.1, 1.0, 0)
+    dims = _lib.Dims(1, 1, 99, 1, 1, 1, 0.1, 1.0, 0, 0)
     import ctypes
     assert L.enflow_flow_workspace_bytes(ctypes.byref(dims), 0) == 0
     assert b'nf=99' in L.enflow_last_error()
