@@ -39,6 +39,53 @@ CONFIGS = {
 }
 
 
+def workload_config(config, batch, world, nf, desc, n_atoms, E):
+    """`config` of the JSON line: describes the WORKLOAD only, identical for the b200 arm and the reference arm (the
+    arm-specific facts - arithmetic mode, launch mode, the CPU sample size - live in their own keys)."""
+    generate = config == 'c4'
+    return {'workload': desc, 'per_gpu_batch': batch, 'global_batch': batch * world, 'atoms_per_gpu': n_atoms,
+            'edges_per_layer_per_gpu': E, 'layers': L_LAYERS, 'hidden': H, 'nf': nf,
+            'step': ('LFIntegrator.reverse (inverse pass with per-molecule log-det, no collective)' if generate else
+                     'LFIntegrator.forward + Alchemical_NLL + backward (all parameter grads) + gradient all-reduce (N > 1) + Adam'),
+            'parallelism': f'dp{world}',
+            'l2': 'no explicit flush: every layer of every step streams far more than the 126 MB L2 through HBM '
+                  '(C2: E*H*4 = 426 MB of edge gradients per layer)'}
+
+
+def static_edge_count(config, arrs):
+    """edges per layer: all ordered pairs for the fully connected configs, else measured once with the oracle-free K0 path"""
+    if config in ('c2', 'c3'):
+        return int((arrs['N'] * (arrs['N'] - 1)).sum())
+    return None
+
+
+NCU_SUMMARY = os.path.join('profiles', 'r2_edge_kernels_summary.csv')
+
+
+def ncu_summary(kernel):
+    """dram traffic per launch and tensor-pipe activity of `kernel` from the committed `ncu --set full` summary of this
+    bench command (profiles/r2_edge_kernels_summary.csv, written by tools/ncu_summary.py); None if not captured."""
+    path = os.path.join(ROOT, NCU_SUMMARY)
+    if not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    for r in rows[1:]:
+        if r and r[0].startswith(kernel):
+            def col(prefix):
+                for i, h in enumerate(hdr):
+                    if h.startswith(prefix):
+                        unit = h[h.index('[') + 1:h.index(']')] if '[' in h else ''
+                        v = float(r[i])
+                        return v * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}.get(unit, 1.0)
+                return None
+            rd, wr = col('dram__bytes_read.sum'), col('dram__bytes_write.sum')
+            return {'traffic': (rd + wr) if rd is not None and wr is not None else None,
+                    'pipe_tensor_active_pct': col('sm__pipe_tensor_cycles_active'), 'ncu_us': col('gpu__time_duration.sum')}
+    return None
+
+
 def edge_flops(E, nf, train):
     """per edge 2H(2nf+1) + 4H^2 + 2H forward; backward = 2x (dgrad + wgrad)."""
     fwd = E * (2 * H * (2 * nf + 1) + 4 * H * H + 2 * H)
@@ -117,21 +164,29 @@ def cpu_port_throughput(config, nf, sample_mols, steps, warmup, kwargs):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host CPU (the reference is pure Python/PyTorch
-    and cannot travel to the GPU box, so the validated port under oracle/ stands in: kind 'port')."""
+    """--impl reference: the reference's own algorithm on the host CPU (the reference is pure Python/PyTorch and cannot
+    travel to the GPU box, so the port under oracle/ - pinned against the unmodified reference by tests/golden - stands
+    in: kind 'port').  Same config / steps / warmup as the b200 arm; each step is a bounded sample of the workload."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     config, batch, kwargs, nf, desc = CONFIGS[args.config]
+    batch = args.batch or batch
+    world = int(os.environ.get('WORLD_SIZE', 1))
     sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c4': 256, 'c5': 1}[args.config]
-    mols_s, cores, sec = cpu_port_throughput(config, nf, sample, args.steps, min(args.warmup, 1), kwargs)
+    arrs = syn.make_batch(config, 2, **kwargs)            # layout only: every bench config has a fixed atom count per molecule
+    n_mol = int(arrs['N'][0])
+    n_atoms = n_mol * batch
+    E = n_mol * (n_mol - 1) * batch if config in ('c2', 'c3') else None      # radius-graph configs: data dependent
+    mols_s, cores, sec = cpu_port_throughput(config, nf, sample, args.steps, args.warmup, kwargs)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': mols_s, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': desc, 'layers': L_LAYERS, 'hidden': H, 'nf': nf},
+        'config': workload_config(config, batch, world, nf, desc, n_atoms, E),
         'cpu_baseline': {'value': mols_s, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': f'{sample} molecules per step of the same config, fp64 torch CPU, all host threads'},
+                         'sample': f'{sample} molecules of the same config per step (per-molecule throughput), fp64 torch CPU, '
+                                   f'all host threads; {args.warmup} warm-up + {args.steps} timed steps'},
         'e2e': {'value': mols_s, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -196,7 +251,8 @@ def main():
     resident = host.to(dev)
     resident.meta()
     n_atoms = int(arrs['N'].sum())
-    E = int((arrs['N'] * (arrs['N'] - 1)).sum()) if config in ('c2', 'c3') else None
+    E_static = static_edge_count(config, arrs)          # all ordered pairs (fully connected configs) or None
+    E = E_static
     h2d = sum(t.numel() * t.element_size() for t in (host.h, host.g, host.pos, host.vel, host.box, host.N, host.r_cut))
 
     def view(d):      # fresh wrapper: forward() rebinds the fields of the Data it is given
@@ -227,30 +283,39 @@ def main():
         step(view(resident))
     model.check_status = False      # capacity is now known; no host sync inside the timed device loop
     barrier()
-    if E is None:
-        E = int(model._edge_caps[(batch, n_atoms)] / 1.25)
+    if E is None:          # radius-graph configs: the first layer's neighbour list, measured
+        E = int(view(resident).build_edges(reference_order=False).row.numel())
 
     # The whole step (forward C call, likelihood, backward C call, all-reduce, Adam) has no host synchronisation, so it
     # is captured once in a CUDA graph and replayed (enflow_b200.graph); --no-graph launches every kernel eagerly.
     L = _lib.lib()
     gstep, graph_note, launches_per_step = None, 'eager launches', None
     # (with more than one rank the NCCL all-reduce is not captured: two graphs with one eager all-reduce between them)
-    if not generate and not args.no_graph:
+    if not args.no_graph:
         try:
-            from enflow_b200.graph import GraphedTrainStep
+            from enflow_b200.graph import GraphedReverse, GraphedTrainStep
             L.enflow_launch_count(1)
-            gstep = GraphedTrainStep(model, nll, opt, resident, warmup=1)
+            if generate:
+                gstep = GraphedReverse(model, resident, warmup=1)
+            else:
+                gstep = GraphedTrainStep(model, nll, opt, resident, warmup=1)
             launches_per_step = int(L.enflow_launch_count(1)) // 2      # 1 eager warm-up + 1 captured step
             graph_note = 'CUDA graph replay of the whole step'
+            if world > 1 and not generate:
+                graph_note += ' (two graphs around one eager NCCL all-reduce of the flat gradient buffer)'
         except Exception as exc:      # keep measuring: eager path
-            gstep, graph_note = None, f'eager launches (graph capture failed: {type(exc).__name__})'
+            gstep, graph_note = None, f'eager launches (graph capture failed: {type(exc).__name__}: {exc})'
             torch.cuda.synchronize()
 
     def run_resident():
-        return gstep() if gstep is not None else step(view(resident))
+        if gstep is None:
+            return step(view(resident))
+        return gstep().neg_ldj_mol.sum() if generate else gstep()
 
     def run_host():          # H2D of the batch from pinned host memory every step
-        return gstep(host) if gstep is not None else step(host.to(dev))
+        if gstep is None:
+            return step(host.to(dev))
+        return gstep(host).neg_ldj_mol.sum() if generate else gstep(host)
 
     # ---- end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
     model.check_status = gstep is None
@@ -303,68 +368,65 @@ def main():
         pk = peaks()
         ms_step = ms_total / args.steps
         mols = batch * world
-        # dominant kernel + the HBM-bound kernels the north star names
+        # one timing family per kernel: average launch duration (CUDA events on the launch stream, eager launches) and
+        # share of the eagerly launched step
         avg = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in fam.items()}
         share = {k: v[0] / ms_eager for k, v in fam.items()}
         dom = max(fam, key=lambda k: fam[k][0])
+        tc_mode = args.precision != 'fp32'
         flops = {'edge_fwd': edge_flops(E, nf, False), 'edge_bwd': 2 * edge_flops(E, nf, False)}
         roof = None
-        if dom not in flops:
-            # the radius-graph / small-batch configs are dominated by K0 (neighbour list): integer + fp64 work whose
-            # algorithmic traffic is the positions in and the edge list out
-            k0_bytes = n_atoms * 24 + E * 8 + (n_atoms + 1) * 4
-            modelled = {'edges': k0_bytes}
-            cand = dom if dom in modelled else max(flops, key=lambda k: fam[k][0])
-            if cand in modelled and avg[cand] > 0:
-                a = modelled[cand] / (avg[cand] * 1e-3) / 1e9
-                roof = {'kernel': 'K0 neighbour list (k_edges_survivors + k_edges_hits x2 + scans)', 'bound': 'hbm',
-                        'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': a / pk['hbm_gbs'], 'traffic': None,
-                        'peak_source': pk['source'] + ' HBM copy bandwidth',
-                        'algorithmic_bytes_per_launch': modelled[cand],
-                        'note': 'dominant kernel family of this config; latency-bound fp64 image tests over 27 n points per '
-                                'molecule, far from the HBM roofline by construction (DESIGN.md section 4)'}
-            else:
-                dom = cand
-        if roof is None and dom in flops and avg[dom] > 0:
+        if dom in flops and avg[dom] > 0:
             ach = flops[dom] / (avg[dom] * 1e-3) / 1e12
-            tc_mode = args.precision != 'fp32'
             kname = 'k_' + dom + ('_tc' if tc_mode else '')
-            # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
-            # (profiles/r1c_edge_kernels_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), C2 shape only
-            traffic = {'k_edge_bwd_tc': 528.5e6, 'k_edge_bwd': 1358.1e6}.get(kname) if args.config == 'c2' and batch == 1024 else None
+            ncu = ncu_summary(kname + ('<1>' if args.precision == 'fp32_tc' else '<0>') if tc_mode else kname) \
+                if (args.config == 'c2' and batch == 1024) else None
             mma_per_gemm = {'fp32': 0, 'fp32_tc': 3, 'bf16': 1}[args.precision]
+            gemms = 6 if dom == 'edge_bwd' else 2
             roof = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_sustained'],
-                    'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
+                    'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'],
+                    'traffic': ncu['traffic'] if ncu else None,
+                    'traffic_source': NCU_SUMMARY + ' (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full '
+                                      'of this command)' if ncu and ncu['traffic'] else None,
+                    'pipe_tensor_active_pct': ncu['pipe_tensor_active_pct'] if ncu else None,
+                    'avg_launch_ms': avg[dom], 'launches_per_step': fam[dom][1] / args.steps,
                     'peak_source': pk['source'] + ' bf16 dense sustained (kernel timed inside a long step)',
                     'algorithmic_flops_per_launch': flops[dom],
-                    'note': ('achieved = algorithmic FLOPs (2x forward: dgrad + wgrad of the two HxH layers) / CUDA-event time. '
-                             f'The tensor pipe executes {mma_per_gemm} bf16 MMA(s) per GEMM term (bf16x3 operand split keeps fp32 '
-                             'parity) and 6 GEMMs per tile (2 recompute + 2 dgrad + 2 wgrad), i.e. '
-                             f'{mma_per_gemm * 1.5:.1f}x the algorithmic FLOPs; the kernel is bound by the SiLU/split epilogues '
-                             '(XU + FMA pipes), see DESIGN.md section 4') if tc_mode else
-                            'fp32 FFMA baseline path: dense layers on the CUDA cores'}
+                    'note': ('achieved = algorithmic FLOPs of the two HxH layers'
+                             + (' (x2: dgrad + wgrad)' if dom == 'edge_bwd' else '') + ' / CUDA-event time of this kernel alone. '
+                             f'The tensor pipe executes {mma_per_gemm} bf16 MMA(s) per GEMM term (the bf16x3 operand split keeps '
+                             f'fp32 parity) and {gemms} GEMMs per tile'
+                             + (' (2 recompute + 2 dgrad + 2 wgrad)' if dom == 'edge_bwd' else '')
+                             + '; pipe_tensor_active_pct is what ncu measured for the executed MMAs. The kernel is bound by the '
+                               'L1/shared-memory data pipe (MMA operand reads + epilogue traffic), DESIGN.md section 4') if tc_mode
+                            else 'fp32 FFMA cross-check path: dense layers on the CUDA cores'}
+        elif avg.get('edges'):
+            # radius-graph / small-batch configs are dominated by K0 (neighbour list): integer + fp64 work whose
+            # algorithmic traffic is the positions in and the edge list out
+            k0_bytes = n_atoms * 24 + E * 8 + (n_atoms + 1) * 4
+            a = k0_bytes / (avg['edges'] * 1e-3) / 1e9
+            roof = {'kernel': 'K0 neighbour list (k_edges_survivors + k_edges_hits x2 + scans)', 'bound': 'hbm',
+                    'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': a / pk['hbm_gbs'], 'traffic': None,
+                    'peak_source': pk['source'] + ' HBM copy bandwidth', 'algorithmic_bytes_per_launch': k0_bytes,
+                    'note': f'dominant family of this config is {dom}; K0 is latency-bound fp64 image tests over 27 n points per '
+                            'molecule, far from the HBM roofline by construction (DESIGN.md section 4)'}
+        # the HBM-bound kernels the north star names (SURVEY 8d byte counts), each from its OWN timing family
+        hbm = {}
         seg_bytes = E * H * 4 + (n_atoms + 1) * 4 + n_atoms * H * 4
         cpl_bytes = n_atoms * (19 + 5 * nf) * 4 + batch * 4
-        hbm = {}
-        if avg.get('segment_sum128'):
-            a = seg_bytes / (avg['segment_sum128'] * 1e-3) / 1e9
-            hbm['k_segment_sum128'] = {'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                       'frac': a / pk['hbm_gbs'], 'bytes': seg_bytes}
-        if avg.get('coupling'):
-            a = cpl_bytes / (avg['coupling'] * 1e-3) / 1e9
-            hbm['k_coupling'] = {'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                 'frac': a / pk['hbm_gbs'], 'bytes': cpl_bytes}
+        for fam_name, kernel, nbytes in (('seg_cols', 'k_segment_sum128<0,1> (dS: column-grouped sum of dz1)', seg_bytes),
+                                         ('coupling_fwd', 'k_coupling_fwd', cpl_bytes)):
+            if avg.get(fam_name):
+                a = nbytes / (avg[fam_name] * 1e-3) / 1e9
+                hbm[fam_name] = {'kernel': kernel, 'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                 'frac': a / pk['hbm_gbs'], 'bytes': nbytes, 'avg_launch_ms': avg[fam_name]}
+        cfg = workload_config(config, batch, world, nf, desc, n_atoms, E_static)
         line = {
             'metric': METRIC, 'value': mols * args.steps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': desc, 'per_gpu_batch': batch, 'global_batch': mols, 'atoms_per_gpu': n_atoms,
-                       'edges_per_layer_per_gpu': E, 'layers': L_LAYERS, 'hidden': H, 'nf': nf, 'edge_mlp': args.precision,
-                       'step': ('LFIntegrator.reverse (inverse pass, no collective)' if generate else
-                                'forward + Alchemical_NLL + backward (all parameter grads)'
-                                + (' + NCCL all-reduce of the flat gradient buffer' if world > 1 else '') + ' + fused Adam on the flat buffers'),
-                       'parallelism': f'dp{world}', 'l2': 'no explicit flush: every layer of every step streams E*H*4 bytes of '
-                       'edge gradients (dz1, 426 MB at this shape) plus the run partials through HBM, far above the 126 MB L2'},
+            'config': cfg,
+            'edge_mlp': args.precision, 'edges_per_layer_measured': E,
             'clocks': clocks,
             'e2e': {'value': mols * args.steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'last_loss': loss_host},
@@ -375,6 +437,9 @@ def main():
             'roofline_hbm_kernels': hbm,
             'kernel_ms_per_step': {k: v[0] / args.steps for k, v in fam.items()},
             'kernel_share_of_step': share,
+            'kernel_timing_note': 'kernel_ms_per_step / kernel_share_of_step come from the eagerly launched pass '
+                                  '(eager_ms_per_step, CUDA events around every kernel family); ms_per_step is the graph replay, '
+                                  'so the family times sum to more than ms_per_step',
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c4': 256, 'c5': 1}[args.config]

@@ -123,8 +123,9 @@ def param_layout(nf, L):
     return int(total), list(offs), list(cnts)
 
 
-TIMING_KINDS = ['edges', 'node_pre', 'edge_fwd', 'segment_sum128', 'segment_sum3', 'node_post', 'coupling',
-                'edge_bwd', 'node_bwd', 'col_perm', 'argmax', 'nll']
+TIMING_KINDS = ['edges', 'node_pre', 'edge_fwd', 'run_sum', 'seg_cols', 'seg_rows', 'segment_sum3', 'node_post', 'coupling_fwd',
+                'coupling_bwd', 'coupling_inv', 'edge_geom', 'edge_bwd', 'edge_reduce', 'node_post_bwd', 'node_pre_bwd',
+                'col_perm', 'argmax', 'nll']
 
 
 def timing_read():

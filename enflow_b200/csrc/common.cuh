@@ -16,8 +16,10 @@
 void enf_set_error(const char* fmt, ...);
 void enf_count_launch();                                  // every kernel launch of this library is counted
 // optional per-kernel-family timing with CUDA events on the launch stream (see enflow_timing_*)
-enum { TK_EDGES = 0, TK_NODE_PRE, TK_EDGE_FWD, TK_SEG128, TK_SEG3, TK_NODE_POST, TK_COUPLING, TK_EDGE_BWD,
-       TK_NODE_BWD, TK_COL_PERM, TK_ARGMAX, TK_NLL, TK_COUNT };
+// one family per kernel (a family that mixes kernels cannot be held against a roofline)
+enum { TK_EDGES = 0, TK_NODE_PRE, TK_EDGE_FWD, TK_RUN_SUM, TK_SEG_COLS, TK_SEG_ROWS, TK_SEG3, TK_NODE_POST, TK_COUPLING_FWD,
+       TK_COUPLING_BWD, TK_COUPLING_INV, TK_EDGE_GEOM, TK_EDGE_BWD, TK_EDGE_REDUCE, TK_NODE_POST_BWD, TK_NODE_PRE_BWD,
+       TK_COL_PERM, TK_ARGMAX, TK_NLL, TK_COUNT };
 void enf_time_begin(int kind, cudaStream_t st);
 void enf_time_end(cudaStream_t st);
 

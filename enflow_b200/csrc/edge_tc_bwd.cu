@@ -690,8 +690,11 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
     const int slots = (E_cap + TE - 1) / TE * TE;
     int ggrid = (slots + 255) / 256;
     if (ggrid > 8 * enf_num_sms()) ggrid = 8 * enf_num_sms();
+    enf_time_begin(TK_EDGE_GEOM, st);
     enf_count_launch(), k_edge_geom_bwd<<<ggrid, 256, 0, st>>>(row, col, rowptr, E_dev, pos, box, s_saved, dF, coords_weight, mis, geom, E_cap);
+    enf_time_end(st);
     const GeomView gv = geom_view(geom, E_cap);
+    enf_time_begin(TK_EDGE_BWD, st);
     if (mode == 1)
         enf_count_launch(), k_edge_bwd_tc<true><<<grid, THREADS, SmemB<true>::total, st>>>(
             gv, E_dev, E_cap, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3], lp + o.off[P_WC], wimg, dagg,
@@ -700,6 +703,10 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
         enf_count_launch(), k_edge_bwd_tc<false><<<grid, THREADS, SmemB<false>::total, st>>>(
             gv, E_dev, E_cap, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3], lp + o.off[P_WC], wimg, dagg,
             runs, dz1, dd, partial, status);
+    enf_time_end(st);
     ENF_CHECK_LAUNCH();
-    return enf_edge_reduce_partials(partial, grid, lgrad, nf, st);
+    enf_time_begin(TK_EDGE_REDUCE, st);
+    const int rc = enf_edge_reduce_partials(partial, grid, lgrad, nf, st);
+    enf_time_end(st);
+    return rc;
 }

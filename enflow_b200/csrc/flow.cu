@@ -153,14 +153,14 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
     if (d.mode == 0) {
         TIMED(TK_EDGE_FWD, enf_edge_fwd(sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, packed, d.nf, w.wr,
                                         sv.z2, sv.z3, sv.s, w.trans, st));
-        TIMED(TK_SEG128, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
+        TIMED(TK_SEG_ROWS, enf_segment_sum128(sv.z2, sv.rowptr, nullptr, d.N, d.E_cap, 1, sv.agg, st));
     } else {
         // tensor-core path: the kernel reduces silu(z2) over each row into per-run partials; no [E,H] store
         if (!d.fc) ENF_TRY(enf_run_index(sv.rowptr, d.N, sv.mis, w.run_scratch, st));
         TIMED(TK_EDGE_FWD, enf_edge_fwd_tc(d.mode, sv.row, sv.col, sv.E_dev, d.E_cap, pos, box, sv.P, sv.S, lp, tcimg, d.nf,
                                            sv.rowptr, sv.mis, w.runs, sv.s, w.trans, st));
         // agg = row sums of the run partials, F = coords_weight * row means of trans (helpers.py:62-70): one launch
-        TIMED(TK_SEG128, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, sv.agg, w.trans, 1, d.coords_weight, 0,
+        TIMED(TK_RUN_SUM, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, sv.agg, w.trans, 1, d.coords_weight, 0,
                                              w.F, st));
     }
     if (d.mode == 0)
@@ -236,7 +236,7 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
         const LayerSave& sv = w.layer[training ? l : 0];
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
                              tc_image(w, l), w.h[cur], w.pos[cur], box, r_cut, mol_off, status, st));
-        TIMED(TK_COUPLING, enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
+        TIMED(TK_COUPLING_FWD, enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
                                  ho, go, po, vo, ldj_mol, st));
     }
     ENF_TRY(enf_ldj_total(ldj_mol, d.B, eps ? w.log_q : nullptr, ldj, st));
@@ -259,13 +259,13 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         const float* lp = layer_params(params, nf, l);
         float* lg = layer_params(grads, nf, l);
         // coupling step (dynamics.py:14-21): gradients w.r.t. Q, F, G and the incoming state
-        TIMED(TK_COUPLING, enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
+        TIMED(TK_COUPLING_BWD, enf_coupling_bwd(sv.Q, w.vel[l], dldj, d.N, nf, d.dt, dh, dg, dpos, dvel, w.dQ, w.dF, w.dG, st));
         // node_model (egcl.py:65-69)
         if (d.mode == 0)
-            TIMED(TK_NODE_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp,
+            TIMED(TK_NODE_POST_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp,
                                                  w.packed + (int64_t)l * enf_pack_offsets(nf).size, w.dagg, dh, lg, w.partial, st));
         else
-            TIMED(TK_NODE_BWD, enf_node_post_bwd_tc(d.mode, w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, tc_image(w, l), w.dagg,
+            TIMED(TK_NODE_POST_BWD, enf_node_post_bwd_tc(d.mode, w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, tc_image(w, l), w.dagg,
                                                     dh, lg, w.partial, st));
         // edge_model + force_model (egcl.py:57-63,71-75); P/S were kept by the forward pass
         // column-grouped view of the edges; reused as is when this layer's list equals the one just processed
@@ -284,18 +284,18 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
             TIMED(TK_EDGE_BWD, enf_edge_bwd(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P, sv.S, lp, nf,
                                             w.wr, sv.z2, sv.z3, sv.s, w.dagg, w.dF, d.coords_weight, w.dz1, w.dd, lg,
                                             w.partial, st));
-            TIMED(TK_SEG128, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
+            TIMED(TK_SEG_ROWS, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
         } else {
-            TIMED(TK_EDGE_BWD, enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
+            ENF_TRY(enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
                                                sv.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
-                                               w.runs, w.dz1, w.dd, lg, w.partial, w.geom, status, st));
+                                               w.runs, w.dz1, w.dd, lg, w.partial, w.geom, status, st));      // (times its three kernels itself)
             // dP and the row half of dpos (coord_diff = pos[row] - pos[col], data/base.py:17: +dd onto row atoms)
-            TIMED(TK_SEG128, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
+            TIMED(TK_RUN_SUM, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
         }
         if (d.mode == 0) TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
         // dS and the column half of dpos (-dd onto col atoms), both through the column permutation
-        TIMED(TK_SEG128, enf_segment_sum128_sum3(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, w.dd, -1.0f, dpos, st));
-        TIMED(TK_NODE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
+        TIMED(TK_SEG_COLS, enf_segment_sum128_sum3(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, w.dd, -1.0f, dpos, st));
+        TIMED(TK_NODE_PRE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
     }
     if (eps)
         TIMED(TK_ARGMAX, enf_argmax_bwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), dh, dldj,
@@ -326,10 +326,10 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
     const LayerSave& sv = w.layer[0];
     if (d.fc) ENF_TRY(fc_lists(d, w, mol_off, 0, status, st));
     for (int l = d.L - 1; l >= 0; --l) {
-        TIMED(TK_COUPLING, enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
+        TIMED(TK_COUPLING_INV, enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
                              tc_image(w, l), h, pos, box, r_cut, mol_off, status, st));                           // :31
-        TIMED(TK_COUPLING, enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
+        TIMED(TK_COUPLING_INV, enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
     }
     if (quantize) ENF_TRY(enf_argmax_reverse(h, d.N, nf, st));                                    // :35
     return ENF_OK;

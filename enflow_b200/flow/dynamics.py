@@ -213,6 +213,7 @@ class LFIntegrator(BaseFlow):
             _lib.check(L.enflow_flow_reverse(ctypes.byref(dims), p(self.flat_params), p(h), p(g), p(pos), p(vel),
                                              p(b['box']), p(b['r_cut']), p(b['off']), p(ws), nbytes, int(quantize and fused_q),
                                              p(neg), p(status), _lib.stream()))
+            self.last_status = status
             code = int(status.item()) if self.check_status else 0
             if code & 8:
                 self._fc_keys[(b['B'], b['N'])] = (False, 0)

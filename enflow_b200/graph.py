@@ -127,3 +127,57 @@ class GraphedTrainStep:
         """True if the captured edge capacity was exceeded in the last replay, or the fully connected regime the capture
         assumed no longer holds (status bits 1 and 8; synchronises)."""
         return bool(int(self.status.item()) & 9)
+
+
+class GraphedReverse:
+    """CUDA-graph replay of ``LFIntegrator.reverse`` (the generate.yaml inverse pass) for batches of one layout.
+
+        inv = GraphedReverse(model, example_batch)       # batch on the device
+        out = inv(batch)                                 # out.h/g/pos/vel, out.neg_ldj_mol: static output buffers
+
+    Same constraints as GraphedTrainStep: fixed layout, edge capacity fixed at capture (``overflowed()`` on demand)."""
+
+    def __init__(self, model, example, quantize=True, warmup=2):
+        if not example.pos.is_cuda:
+            raise RuntimeError('GraphedReverse needs the example batch on the CUDA device')
+        self.model, self.quantize = model, quantize
+        f32 = lambda t: t.detach().to(torch.float32).contiguous().clone()
+        self.static = Data(z=example.z, h=f32(example.h), g=f32(example.g), pos=f32(example.pos), vel=f32(example.vel),
+                           N=example.N.clone(), r_cut=example.r_cut.detach().to(example.pos.device, torch.float32).clone(),
+                           box=f32(example.box), label=example.label, device=example.device)
+        B, off, max_n, n_cpu = example.meta()
+        self.static._meta = (B, off.clone(), max_n, n_cpu.clone())
+        self._n_cpu = n_cpu.clone()
+        check = model.check_status
+        model.check_status = True
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):
+                model.reverse(self._view(), quantize=quantize)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        model.check_status = False
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = model.reverse(self._view(), quantize=quantize)
+        self.status = model.last_status
+        model.check_status = check
+
+    def _view(self):
+        d = self.static
+        v = Data(z=d.z, h=d.h, g=d.g, pos=d.pos, vel=d.vel, N=d.N, r_cut=d.r_cut, box=d.box, label=d.label, device=d.device)
+        v._meta = d._meta
+        return v
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            s = self.static
+            for name in ('h', 'g', 'pos', 'vel', 'box'):
+                getattr(s, name).copy_(getattr(batch, name), non_blocking=True)
+            s.r_cut.copy_(batch.r_cut.reshape(-1), non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    def overflowed(self):
+        return bool(int(self.status.item()) & 9)

@@ -51,8 +51,10 @@ int enflow_hidden(void);
  * enflow_launch_count: kernels launched by this library since the last reset.
  * enflow_timing_*: when enabled, the flow entry points bracket each kernel family with CUDA events on
  * the launch stream; enflow_timing_read sums the elapsed milliseconds per family (host arrays of
- * enflow_timing_kinds() entries; order: edges, node_pre, edge_fwd, segment_sum128, segment_sum3,
- * node_post, coupling, edge_bwd, node_bwd, col_perm, argmax, nll). */
+ * enflow_timing_kinds() entries; one family per kernel, order: edges (K0 or the fully connected list + its per-layer
+ * check), node_pre, edge_fwd, run_sum (k_run_sum128), seg_cols (the column-grouped k_segment_sum128 behind dS),
+ * seg_rows (row-grouped k_segment_sum128, FFMA mode), segment_sum3, node_post, coupling_fwd, coupling_bwd, coupling_inv,
+ * edge_geom, edge_bwd (the backward edge kernel alone), edge_reduce, node_post_bwd, node_pre_bwd, col_perm, argmax, nll). */
 long long enflow_launch_count(int reset);
 int enflow_timing_enable(int enable);
 int enflow_timing_kinds(void);
