@@ -278,9 +278,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    dbg = (lambda m: print(f'[bench dbg rank {rank}] {m}', file=sys.stderr, flush=True)) if os.environ.get('ENFLOW_GRAPH_DEBUG') \
+        else (lambda m: None)
     model.check_status = True
     for _ in range(args.warmup):
         step(view(resident))
+    dbg('eager warm-up done')
     model.check_status = False      # capacity is now known; no host sync inside the timed device loop
     barrier()
     if E is None:          # radius-graph configs: the first layer's neighbour list, measured
@@ -302,7 +305,8 @@ def main():
             launches_per_step = int(L.enflow_launch_count(1)) // 2      # 1 eager warm-up + 1 captured step
             graph_note = 'CUDA graph replay of the whole step'
             if world > 1 and not generate:
-                graph_note += ' (two graphs around one eager NCCL all-reduce of the flat gradient buffer)'
+                graph_note += (' (two graphs around one eager NCCL all-reduce of the flat gradient buffer)' if gstep.dp_eager
+                               else ' (ONE graph: the NCCL all-reduce of the flat gradient buffer is captured with the kernels)')
         except Exception as exc:      # keep measuring: eager path
             gstep, graph_note = None, f'eager launches (graph capture failed: {type(exc).__name__}: {exc})'
             torch.cuda.synchronize()
@@ -318,6 +322,7 @@ def main():
         return gstep(host).neg_ldj_mol.sum() if generate else gstep(host)
 
     # ---- end-to-end through the public API with host buffers: H2D of the batch + D2H of the loss every step
+    dbg(f'graph built: {graph_note}')
     model.check_status = gstep is None
     for _ in range(args.warmup):       # warm the host-buffer path too (allocator growth for the per-step device batch)
         run_host().item()
@@ -327,6 +332,7 @@ def main():
         loss_host = run_host().item()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    dbg('e2e loop done')
     model.check_status = False
 
     # ---- device-timed region: inputs resident in HBM, K steps between CUDA events
@@ -336,12 +342,15 @@ def main():
         time.sleep(0.5)        # let nvidia-smi spin up so samples fall inside the (short) timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     L.enflow_launch_count(1)
+    dbg('before timed barrier')
     barrier()
+    dbg('timed loop')
     ev0.record()
     for _ in range(args.steps):
         run_resident()
     ev1.record()
     barrier()
+    dbg('timed loop done')
     ms_total = ev0.elapsed_time(ev1)
     launches = launches_per_step * args.steps if gstep is not None else int(L.enflow_launch_count(1))
     clocks = sampler.stop() if rank == 0 else None
@@ -355,14 +364,17 @@ def main():
         step(view(resident))
     ev3.record()
     barrier()
+    dbg('eager kernel-timing loop done')
     ms_eager = ev2.elapsed_time(ev3)
     fam = _lib.timing_read()
     L.enflow_timing_enable(0)
+    dbg('timing read')
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0]), float(t[1])
+    dbg('max over ranks done')
 
     if rank == 0:
         pk = peaks()
@@ -449,7 +461,20 @@ def main():
                                               f'of the reference algorithm (oracle/), 1 warm-up + 2 timed steps'}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear down: the graphs that captured the gradient all-reduce go first (destroying an NCCL communicator while a
+        # captured graph still references it does not return); if the teardown stalls anyway, leave without it
+        import gc
+        gstep = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        done = threading.Event()
+        threading.Thread(target=lambda: (dist.destroy_process_group(), done.set()), daemon=True).start()
+        if not done.wait(20.0):
+            dbg('destroy_process_group stalled: exiting without it')
+            sys.stdout.flush()
+            os._exit(0)
+        dbg('process group destroyed')
 
 
 if __name__ == '__main__':

@@ -11,8 +11,15 @@ interval, discard, softening, cutoff (in sigma), gap, node_nf, log, traj; `seed`
 What is and is not the same as upstream: potential, cutoff, minimum image, integrator scheme, friction and the
 frame schedule follow the reference's configuration; the energy minimiser is a capped steepest descent instead
 of OpenMM's L-BFGS; the random streams differ (Philox here), so frames agree in distribution, not bit for bit.
-Time is converted with the reference's own `time_to_lj` and the particles have unit mass, i.e. the frames sample
-exp(-(U + |v|^2/2)/kBT), the density `Alchemical_NLL` assigns to (pos, vel) (`enflow/flow/loss.py:16-22`).
+The run advances PHYSICAL time like OpenMM does upstream: the step is dt / tau with tau = sigma sqrt(M/eps) = 4.405 ps
+(`time_to_lj_physical`; the reference's own `time_to_lj`, which it applies to the flow's dt, carries an amu-for-kg slip
+and is 31.6 times smaller: with it 2000 steps of 4 fs moved the atoms ~0.2 sigma off the minimised lattice instead of
+equilibrating the fluid).  Particles have unit mass, so velocities come out with <v^2> = kBT per component, the kinetic
+term `Alchemical_NLL` assigns (`enflow/flow/loss.py:16-22`); positions sample the periodic, cut-off soft-LJ fluid of
+`enflow/data/lj.py:65-76` ((s + r) softening, cutoff 3 sigma), which is the reference's prior but not literally the
+non-periodic r^2 + s expression inside the likelihood.  Parity unpinned: OpenMM is not available here and the
+reference holds no vectors for this path; tests check forces/trajectories against the oracle's restatement, the
+thermostat and the potential-energy plateau statistically.
 """
 import math
 
@@ -20,7 +27,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..utils.conversion import dist_to_lj, kelvin_to_lj, time_to_lj, lj_to_dist
+from ..utils.conversion import dist_to_lj, kelvin_to_lj, time_to_lj_physical, lj_to_dist
 from ..utils.helpers import apply_pbc
 from .base import Data
 
@@ -53,7 +60,7 @@ class LJDataset:
         box_lj = np.array([dist_to_lj(float(b), dist_unit) for b in box], dtype=np.float64)
         gap_lj = dist_to_lj(float(gap), dist_unit)
         kBT = kelvin_to_lj(float(temp))
-        dt_lj = time_to_lj(float(dt), time_unit)
+        dt_lj = time_to_lj_physical(float(dt), time_unit)      # OpenMM's physical step in units of tau (see module docstring)
         # friction is per picosecond (`simulated.py:109`: friction/(scale*ps)), dt in `time_unit`: a = exp(-gamma dt)
         dt_ps = float(dt) * (1.0 if time_unit == 'pico' else 1e-3)
         a = math.exp(-float(friction) * dt_ps)

@@ -234,10 +234,88 @@ class LFIntegrator(BaseFlow):
 
 
 class VVIntegrator(BaseFlow):
-    """`dynamics.py:39-86` is dead code upstream (forward raises TypeError, reverse calls a missing
-    method); there is nothing to be in parity with, so it is not provided."""
+    """`dynamics.py:39-86`, the velocity-Verlet variant, as a FIXED-FORWARD plugin.
 
-    def forward(self, data):
-        raise NotImplementedError('VVIntegrator cannot run in the reference (enflow/flow/dynamics.py:46-48,85)')
+    Upstream this class cannot run: ``forward`` binds the (z, log_q) tuple of the dequantiser to ``data.h`` (TypeError at
+    the first network call, :47-49), ``reverse`` calls a ``self.quantize`` that does not exist (:85) and both read a
+    ``self.n_iter`` nothing sets (:42,51,69).  Here those three defects are repaired and nothing else is changed:
+    ``data.h, log_q = self.dequantize(data.h)`` with ``log_q`` added to the log-det like `LFIntegrator` does (:11),
+    ``self.dequantize.reverse`` for the final quantisation (what :35 does), and ``n_iter = len(networks) - 1`` (the
+    class evaluates ``n_iter + 1`` networks, :42).  The update rules and the log-det bookkeeping (``ldj += Q`` per
+    network, :50,64) are upstream's, kept as written.
 
-    reverse = forward
+    There is no reference output to be in parity with, so the plugin is validated by what can be checked without one
+    (tests/test_gpu_vv.py): ``reverse(forward(x)) == x``, rotation / translation / permutation equivariance in the
+    well-defined regime, determinism.  Every network evaluation is the stand-alone EGCL kernel path (one neighbour
+    list + the K1/K2/node kernels per call); the leap-frog algebra between them is a handful of elementwise torch ops on
+    the device.  Inference only: the stand-alone EGCL path records no autograd, so calling it with autograd enabled
+    raises instead of returning a loss that silently ignores the networks.
+    """
+
+    def __init__(self, networks, dequant_network, dt):
+        super().__init__(networks, dequant_network, dt)
+        if len(networks) < 2:
+            raise ValueError('VVIntegrator evaluates n_iter + 1 networks (dynamics.py:42): give it at least two')
+        self.n_iter = len(networks) - 1
+        self.precision = 'fp32_tc'
+
+    def make_networks(self, network):                       # dynamics.py:40-43
+        return [network for _ in range(self.n_iter + 1)]
+
+    def _net(self, i, data):
+        net = self.networks[i]
+        net.precision = self.precision
+        Q, F, G = net(data.h, data.edges)
+        dt = data.pos.dtype
+        return Q.to(dt), F.to(dt), G.to(dt)
+
+    def _guard(self):
+        if torch.is_grad_enabled():
+            raise NotImplementedError('enflow_b200 VVIntegrator is an inference-only plugin (dead code upstream, no oracle): '
+                                      'call it under torch.no_grad(); train with LFIntegrator')
+
+    def forward(self, data, eps=None, dequantize=True):
+        self._guard()
+        ldj = 0
+        if dequantize:
+            from ..nn.argmax import ArgMax
+            if isinstance(self.dequantize, ArgMax):
+                B, off, _, _ = data.meta()
+                data.h, log_q = self.dequantize(data.h, eps=eps, mol_off=off)
+            else:
+                data.h, log_q = self.dequantize(data.h)
+            data.h = data.h.to(data.pos.dtype)
+            ldj = log_q
+        Q, F, G = self._net(0, data)
+        ldj = ldj + Q.sum()
+        for i in range(1, self.n_iter + 1):
+            scale = 0.5 * (1 + torch.exp(Q))
+            data.vel = scale * data.vel + F * self.dt_2
+            data.g = data.g + G * self.dt_2
+            data.pos = data.pos + data.vel * self.dt
+            data.pbc()
+            data.h = data.h + data.g * self.dt
+            Q, F, G = self._net(i, data)
+            scale = 0.5 * (torch.exp(Q) - 1)
+            data.vel = (data.vel + F * self.dt_2) / (1 - scale)
+            data.g = data.g + G * self.dt_2
+            ldj = ldj + Q.sum()
+        return data, ldj
+
+    def reverse(self, data, quantize=True):
+        self._guard()
+        Q, F, G = self._net(self.n_iter, data)
+        for i in reversed(range(0, self.n_iter)):
+            data.g = data.g - G * self.dt_2
+            scale = 0.5 * (torch.exp(Q) - 1)
+            data.vel = data.vel * (1 - scale) - F * self.dt_2
+            data.h = data.h - data.g * self.dt
+            data.pos = data.pos - data.vel * self.dt
+            data.pbc()
+            Q, F, G = self._net(i, data)
+            data.g = data.g - G * self.dt_2
+            scale = 0.5 * (1 + torch.exp(Q))
+            data.vel = (data.vel - F * self.dt_2) / scale
+        if quantize:
+            data.h = self.dequantize.reverse(data.h)
+        return data

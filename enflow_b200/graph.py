@@ -61,10 +61,53 @@ class GraphedTrainStep:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
             pass
-        # Data parallel: the NCCL all-reduce is NOT captured.  Two graphs (everything up to the gradients; the
-        # optimizer) with one eager all-reduce of the flat gradient buffer between their replays.
+        # Data parallel: the gradient all-reduce (issued from the flow's backward node, NCCL AVG over the flat buffer) is
+        # captured with everything else: ONE graph per step, as on a single GPU.  Should the capture of the collective
+        # fail (an NCCL build without graph support), fall back to two graphs (everything up to the gradients; the
+        # optimizer) with one eager all-reduce between their replays.
         self.dp = getattr(model, '_dp_group', None) is not None
-        self.split = self.dp or self.check_overflow      # gradients and optimizer as two graphs
+        self.split = self.check_overflow                 # gradients and optimizer as two graphs
+        self.dp_eager = False
+        if self.dp and not self.split:
+            import torch.distributed as dist
+            ok, g1, loss1 = True, torch.cuda.CUDAGraph(), None
+            import os, sys
+            dbg = (lambda m: print(f'[graph dbg rank {dist.get_rank()}] {m}', file=sys.stderr, flush=True)) \
+                if os.environ.get('ENFLOW_GRAPH_DEBUG') else (lambda m: None)
+            dbg('capturing single graph')
+            # the captured collective gets a communicator of its own: eager collectives on the training group (logging
+            # all-reduce, barriers, an eagerly launched step of another layout) then never interleave with graph replays
+            # on one NCCL communicator
+            train_group = model._dp_group
+            if getattr(model, '_dp_graph_group', None) is None:
+                model._dp_graph_group = dist.new_group(ranks=list(range(dist.get_world_size(train_group))))
+                warm = torch.zeros(1, device=example.pos.device)
+                dist.all_reduce(warm, group=model._dp_graph_group)      # create the communicator before capturing on it
+                torch.cuda.synchronize()
+            model._dp_group = model._dp_graph_group
+            try:
+                # thread-local capture mode: the NCCL watchdog thread queries events while this thread captures
+                with torch.cuda.graph(g1, capture_error_mode='thread_local'):
+                    loss1 = self._step_body()
+            except Exception as exc:                     # noqa: BLE001 - keep training: two-graph form below
+                ok = False
+                dbg(f'capture failed: {type(exc).__name__}: {exc}')
+                torch.cuda.synchronize()
+            model._dp_group = train_group
+            dbg(f'capture done ok={ok}')
+            # every rank must replay the same form: one that failed to capture the collective takes all of them along
+            agree = torch.tensor([1.0 if ok else 0.0], device=example.pos.device)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=model._dp_group)
+            dbg(f'agree={float(agree.item())}')
+            if float(agree.item()) >= 1.0:
+                self.graph, self.loss = g1, loss1
+                self.status = model.last_status
+                model.check_status = self._check
+                return
+            del g1, loss1
+            self.split = self.dp_eager = True
+        elif self.dp:
+            self.dp_eager = True
         self.graph = torch.cuda.CUDAGraph()
         if self.split:
             model._dp_defer = True
@@ -117,7 +160,7 @@ class GraphedTrainStep:
         if self.split:
             if self.check_overflow and self.overflowed():
                 raise EdgeCapacityOverflow('edge capacity captured in the CUDA graph exceeded by this batch')
-            if self.dp:
+            if self.dp_eager:
                 from .parallel import allreduce_mean_
                 allreduce_mean_(self.model.flat_grads, self.model._dp_group)
             self.graph_opt.replay()

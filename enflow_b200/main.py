@@ -240,5 +240,9 @@ class Main:
         elif self.mode == 'gen':
             res = self.generate()
         if self.ddp:
+            self._gstep = None                  # captured graphs reference the NCCL communicator: release them first
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return res

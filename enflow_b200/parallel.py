@@ -17,9 +17,13 @@ def init_data_parallel(flow, group=None, src=0):
 
 
 def allreduce_mean_(flat, group):
-    """In-place mean over ranks of a flat buffer (NCCL on GPUs over NVLink/NVSwitch; gloo in the CPU tests)."""
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.mul_(1.0 / dist.get_world_size(group))
+    """In-place mean over ranks of a flat buffer: ONE collective (NCCL's AVG over NVLink/NVSwitch on GPUs, which is also
+    what a captured CUDA graph replays; SUM followed by a scale under gloo, which has no AVG, in the CPU tests)."""
+    if flat.is_cuda and dist.get_backend(group) == 'nccl':
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / dist.get_world_size(group))
     return flat
 
 

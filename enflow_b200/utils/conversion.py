@@ -31,6 +31,14 @@ def time_to_lj(t, unit='pico'):
     return second_to_lj(t * _TIME[unit])
 
 
+def time_to_lj_physical(t, unit='pico'):
+    """Time in the physical reduced unit tau = sigma sqrt(M / eps) with M in kg/mol (4.405 ps for argon).
+    `second_to_lj` above keeps the reference's convention (conversion.py:14-15 divides J/mol by amu, i.e. g/mol) and is
+    sqrt(1000) = 31.6 times smaller; the reference applies it to the flow's dt, while its prior sampler (OpenMM,
+    simulated.py:109) advances physical time.  The GPU sampler follows OpenMM: it integrates with THIS step."""
+    return t * _TIME[unit] / (SIGMA_M * math.sqrt(AR_MASS_AMU * 1e-3 / EPS_J_PER_MOL))
+
+
 def dist_to_lj(x, unit='ang'):
     return meter_to_lj(x * _LEN[unit])
 

@@ -90,6 +90,14 @@ def test_dataset_samples_the_prior_and_feeds_reverse():
     assert len(ds) == 21 and ds.node_nf == 4 and ds.num_atoms_per_mol == 256
     temps = np.array([t for _, _, t in ds.log])
     assert abs(temps.mean() / kBT - 1.0) < 0.05, temps.mean()
+    # equilibrated fluid, not a lattice that has barely moved: the potential energy has left the minimised value and
+    # sits on a plateau (second half of the frames: no drift beyond the fluctuations), and the atoms have diffused
+    pot = np.array([u for _, u, _ in ds.log]) / 256
+    half = len(pot) // 2
+    a, b = pot[half:half + half // 2], pot[half + half // 2:]
+    assert abs(a.mean() - b.mean()) < 4 * max(pot[half:].std(), 1e-3), (a.mean(), b.mean(), pot[half:].std())
+    msd = float(((ds[20].pos - ds[0].pos).double() ** 2).sum(-1).mean())
+    assert msd > 0.05, msd
     d = ds[5]
     assert d.pos.shape == (256, 3) and d.vel.shape == (256, 3) and d.h.shape == (256, 4)
     assert float(d.pos.abs().max()) <= 7.0 / 2 + 7.0 / 2        # centred, inside one cell width of the origin
