@@ -46,7 +46,7 @@ class ArgMax(nn.Module):
         N, nf = int(h.shape[0]), self.node_nf
         if eps is None:
             eps = torch.randn(h.size(), device=dev)
-        hf, ef = _lib.f32c(h), _lib.f32c(eps)
+        hf, ef = _lib.f32c(h), _lib.f32c(eps.to(dev))
         if mol_off is None:
             mol_off = torch.tensor([0, N], dtype=torch.int32, device=dev)
         B = int(mol_off.numel()) - 1
