@@ -26,6 +26,9 @@ def _vv(nf, L, precision='fp32_tc', seed=3):
 def test_vv_round_trip(config, kw):
     from enflow_b200.data import synthetic as syn
     arrs = syn.make_batch(config, 5, seed=21, **kw)
+    # start inside the primary cell: the inverse evaluates network 0 on WRAPPED positions (data.pbc()), and the reference's
+    # neighbour list is not invariant under box translations, so an unwrapped start has no exact inverse
+    arrs['pos'] = arrs['pos'] - np.round(arrs['pos'] / arrs['box']) * arrs['box']
     nf = arrs['h'].shape[1]
     m = _vv(nf, 4)
     assert m.n_iter == 3
