@@ -17,12 +17,13 @@
 // every thread handles one hidden unit x 32 consecutive edges; x1 is produced one warp per edge row.
 // Tiles are software-pipelined per CTA (geometry two tiles ahead, z1 gather and first MMA one tile ahead), see the
 // comment in front of the tile loop and profiles/r1c_phase_times.txt.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int THREADS = 512;
+constexpr int THREADS_V1 = 512;
 
 struct TileInfo {
     int row[tc::TILE], col[tc::TILE], valid[tc::TILE], start[tc::TILE], mis[tc::TILE];
@@ -106,8 +107,8 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // its bias/weight scalars in registers, stores z rows fully coalesced (lanes = consecutive n), and writes the
 // next operand as the [hidden][edge] image (16-byte vector stores) that the second GEMM reads MN-major.
 template <bool SPLIT>
-__global__ void __launch_bounds__(THREADS, 1)
-k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ E_dev,
+__global__ void __launch_bounds__(THREADS_V1, 1)
+k_edge_fwd_tc_v1(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ E_dev,
               const float* __restrict__ pos, const float* __restrict__ box, const float* __restrict__ P,
               const float* __restrict__ S, const float* __restrict__ W1, int e1, const float* __restrict__ b2,
               const float* __restrict__ b3, const float* __restrict__ wc, const unsigned char* __restrict__ wimg,
@@ -356,27 +357,34 @@ int enf_tc_pack_layers(const float* lp0, int nf, int L, int64_t param_stride, un
     return enf_node_tc_pack(lp0, nf, L, param_stride, img0, img_stride, st);
 }
 
-// mode 1 = split (fp32-accurate), mode 2 = bf16
+int enf_edge_fwd_tc_v2(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
+                       const float* box, const float* P, const float* S, const float* lp, int nf, const int* rowptr,
+                       const int* mis, float* runs, float* s_out, float* trans, cudaStream_t st);
+
+// mode 1 = split (fp32-accurate), mode 2 = bf16.  The product kernel is edge_tc_fwd.cu (weights in TMEM, two tiles in
+// flight); ENFLOW_FWD_V1=1 selects the round-1 kernel above for A/B timing.
 int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
                     const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
                     int nf, const int* rowptr, const int* mis, float* runs, float* s_out, float* trans,
                     cudaStream_t st) {
     if (E_cap == 0) return ENF_OK;
+    static const bool v1 = getenv("ENFLOW_FWD_V1") != nullptr;
+    if (!v1) return enf_edge_fwd_tc_v2(mode, row, col, E_dev, E_cap, pos, box, P, S, lp, nf, rowptr, mis, runs, s_out, trans, st);
     const EgclOffsets o = enf_egcl_offsets(nf);
     int grid = (E_cap + tc::TILE - 1) / tc::TILE;
     if (grid > enf_num_sms()) grid = enf_num_sms();
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_edge_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<true>::total);
-        cudaFuncSetAttribute(k_edge_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<false>::total);
+        cudaFuncSetAttribute(k_edge_fwd_tc_v1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<true>::total);
+        cudaFuncSetAttribute(k_edge_fwd_tc_v1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<false>::total);
         attr = true;
     }
     if (mode == 1)
-        enf_count_launch(), k_edge_fwd_tc<true><<<grid, THREADS, Smem<true>::total, st>>>(
+        enf_count_launch(), k_edge_fwd_tc_v1<true><<<grid, THREADS_V1, Smem<true>::total, st>>>(
             row, col, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
             lp + o.off[P_WC], wimg, rowptr, mis, runs, s_out, trans);
     else
-        enf_count_launch(), k_edge_fwd_tc<false><<<grid, THREADS, Smem<false>::total, st>>>(
+        enf_count_launch(), k_edge_fwd_tc_v1<false><<<grid, THREADS_V1, Smem<false>::total, st>>>(
             row, col, E_dev, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_B2], lp + o.off[P_B3],
             lp + o.off[P_WC], wimg, rowptr, mis, runs, s_out, trans);
     ENF_CHECK_LAUNCH();
