@@ -189,23 +189,6 @@ __device__ __forceinline__ void store8(unsigned char* img, uint32_t off, const f
     }
 }
 
-// sum over the 32 lanes of 16 per-lane values; lane l receives column (l & 15)
-__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) {
-        const bool up = lane & off;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = up ? v[i] : v[i + off];
-            const float keep = up ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
-
 // Per-CTA partial layout (floats), identical to the FFMA kernel: dW2 [H*H] | dW3 [H*H] | db2 | db3 | dwc | dwr
 constexpr int EDGE_PARTIAL = 2 * ENF_H * ENF_H + 4 * ENF_H;
 
@@ -572,27 +555,27 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
                 float ds1[16];
                 tc::tmem_ld16(lane_base + PARK_COL + 64 * p + ec, ds1);
                 // dz1 = dx1 * silu'(z1): stored per edge (for the column-grouped sum dS) and reduced over each row's
-                // edges into per-run partials (dP, see segment.cu) by a thread-local running sum
-                int rid = hdr.x;
-                float acc = 0.f;
+                // edges into per-run partials (dP, see segment.cu; tc::run_sums16)
                 const int nvalid = E - (e0 + ec);                     // edges [0, nvalid) of this thread's 16 exist
                 float* dzp = dz1 + (int64_t)(e0 + ec) * ENF_H + n;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float dz = v[j] * ds1[j];
-                    if (j < nvalid) dzp[(int64_t)j * ENF_H] = dz;
-                    if (j > 0 && ((hdr.y >> j) & 1)) {
-                        runs[(int64_t)rid * ENF_H + n] = acc;
-                        ++rid;
-                        acc = 0.f;
-                    }
-                    acc += dz;
-                    gwr = fmaf(dz, rv[j], gwr);
-                    v[j] = wrn * dz;
+                    v[j] *= ds1[j];
+                    gwr = fmaf(v[j], rv[j], gwr);
                 }
-                if (hdr.x >= 0) runs[(int64_t)rid * ENF_H + n] = acc;
-                const float tsum = warp_transpose_sum16(v, lane);
-                if (lane < 16) drp[q * TE + ec + lane] = tsum;
+                if (nvalid >= 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dzp[(int64_t)j * ENF_H] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < nvalid) dzp[(int64_t)j * ENF_H] = v[j];
+                }
+                tc::run_sums16(v, hdr.x, (unsigned)hdr.y, nvalid, runs, n);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= wrn;
+                const float tsum = tc::warp_transpose_sum16(v, lane);
+                if (!(lane & 1)) drp[q * TE + ec + (lane >> 1)] = tsum;
                 tc::named_bar_sync(1 + cg, 128);                     // the four quarter-warps of this edge group
                 if (lane < 4 && e0 + md < E) {
                     const float dr2 = 2.0f * ((drp[md] + drp[TE + md]) + (drp[2 * TE + md] + drp[3 * TE + md]));

@@ -86,23 +86,6 @@ __device__ __forceinline__ void issue_gemm_ts(bool leader, uint32_t tmem_d, uint
     }
 }
 
-// sum over the 32 lanes of 16 per-lane values; lane l receives column (l & 15)
-__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
-#pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) {
-        const bool up = lane & off;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = up ? v[i] : v[i + off];
-            const float keep = up ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
-
 // 8 consecutive edge columns of image row n ([hidden][edge] image, 128 rows x 128 columns)
 template <bool SPLIT>
 __device__ __forceinline__ void store_chunk(unsigned char* A, int n, int chunk16, const float (&x)[8]) {
@@ -350,24 +333,16 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             float v[32];
             tc::tmem_ld32(lane_base + 128u * p + ec, v);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int jb = 16 * half;
-                const int nvalid = E - (e0 + ec + jb);
-                int rid = hd[half].x;
-                float acc = 0.f;
+            for (int j = 0; j < 32; ++j) {
+                const float z = v[j] + b2n;
+                v[j] = z * tc::sigmoid_sfu(z);
+            }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float z = v[jb + j] + b2n;
-                    const float x = z * tc::sigmoid_sfu(z);
-                    v[jb + j] = x;
-                    if (j > 0 && ((hd[half].y >> j) & 1)) {
-                        runs[(int64_t)rid * ENF_H + n] = acc;
-                        ++rid;
-                        acc = 0.f;
-                    }
-                    acc += j < nvalid ? x : 0.f;
-                }
-                if (hd[half].x >= 0) runs[(int64_t)rid * ENF_H + n] = acc;
+            for (int half = 0; half < 2; ++half) {
+                float x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = v[16 * half + j];
+                tc::run_sums16(x, hd[half].x, (unsigned)hd[half].y, E - (e0 + ec + 16 * half), runs, n);
             }
             unsigned char* X = XB + p * L::XBUF;
 #pragma unroll
@@ -398,8 +373,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                         const float y = v[j] + b3n;
                         v[j] = wcn * (y * tc::sigmoid_sfu(y));
                     }
-                    const float tsum = warp_transpose_sum16(v, lane);
-                    if (lane < 16) sp[q * TE + ec + 16 * half + lane] = tsum;
+                    const float tsum = tc::warp_transpose_sum16(v, lane);
+                    if (!(lane & 1)) sp[q * TE + ec + 16 * half + (lane >> 1)] = tsum;
                 }
             }
             if (has_x) {                                           // G2(t) has completed: the buffer is free

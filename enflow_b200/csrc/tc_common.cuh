@@ -256,6 +256,63 @@ __device__ __forceinline__ float sigmoid_sfu(float x) {
     return r;
 }
 
+
+// ---- per-thread helpers of the edge-kernel epilogues ---------------------------------------------------------
+// sum over the 32 lanes of 16 per-lane values by recursive halving (16 shuffles): lane l receives column (l >> 1)
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 2; off >>= 1) {          // lane bit `off` selects which half of the remaining values it keeps
+        const bool up = lane & off;
+        const int h = off >> 1;                        // values kept after this step
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Row sums of one thread's 16 consecutive edges as run partials (segment.cu): `run0` = run id of the first edge (< 0: the
+// group holds no valid edge), `bits` = row-start flags, `nvalid` = how many of the 16 edges exist.  The header is
+// warp-uniform, so the three cases are real branches: no row start inside the group (one sum), exactly one (two
+// predicated sums), anything else or a ragged group (running sum flushed at every start).  The per-edge predicated
+// flush alone cost 12 instructions per element.
+__device__ __forceinline__ void run_sums16(const float (&x)[16], int run0, unsigned bits, int nvalid, float* __restrict__ runs,
+                                           int n) {
+    const unsigned inner = bits & 0xfffeu;
+    float* rp = runs + (int64_t)run0 * 128 + n;
+    if (nvalid >= 16 && inner == 0) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = x[2 * j] + x[2 * j + 1];
+        *rp = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    } else if (nvalid >= 16 && (inner & (inner - 1)) == 0) {
+        const int js = __ffs(inner) - 1;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < js) a0 += x[j];
+            else a1 += x[j];
+        }
+        rp[0] = a0;
+        rp[128] = a1;
+    } else if (run0 >= 0) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j > 0 && ((inner >> j) & 1)) {
+                *rp = acc;
+                rp += 128;
+                acc = 0.f;
+            }
+            acc += j < nvalid ? x[j] : 0.f;
+        }
+        *rp = acc;
+    }
+}
+
 template <bool SPLIT, int KS, typename OA, typename OB>
 __device__ __forceinline__ void issue_gemm_t(uint32_t tmem_d, uint64_t a, uint32_t a_lo_bytes, uint64_t b,
                                              uint32_t b_lo_bytes, uint32_t idesc, bool acc_first) {
