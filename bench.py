@@ -6,7 +6,8 @@
 
 One JSON line on stdout (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through
 the public API with pinned HOST buffers (H2D of the batch and D2H of the loss inside the timed region).
-`--impl reference` times the CPU port of the reference algorithm (oracle/) on the host cores.
+`--impl reference` times the reference's own CPU path (baseline/_ref, vendored by build(); else the port under oracle/)
+on the host cores.
 """
 import argparse
 import json
@@ -142,31 +143,86 @@ class ClockSampler:
                 'samples': len(rows), 'reasons': reasons}
 
 
-def cpu_port_throughput(config, nf, sample_mols, steps, warmup, kwargs):
-    """Time the CPU port of the reference algorithm (oracle/) on a bounded sample. Checker code used as
-    the reported baseline only; never on the product path."""
-    from oracle import enflow_oracle as orc
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')      # the unmodified reference tree + a 2-file rdkit stub (build())
+
+
+def _import_reference():
+    """enflow.* of the UNMODIFIED reference, vendored by __graft_entry__.build() to baseline/_ref (git-ignored, travels to the
+    GPU box).  None when it was never vendored (the port under oracle/ then stands in)."""
+    if not os.path.exists(os.path.join(REF_DIR, 'enflow', 'flow', 'dynamics.py')):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import enflow.data.base as rbase
+    import enflow.flow.dynamics as rdyn
+    import enflow.flow.loss as rloss
+    import enflow.nn.argmax as rargmax
+    import enflow.nn.egcl as regcl
+    return rbase, regcl, rargmax, rdyn, rloss
+
+
+def cpu_reference_throughput(config, nf, sample_mols, steps, warmup, kwargs):
+    """Time the reference's own CPU path (fp64 PyTorch, all host threads) on a bounded sample of the workload:
+    enflow/main.py:150-153 model, batch through DataLoader.collater (data/base.py:162-174), LFIntegrator.forward +
+    Alchemical_NLL + backward (main.py:219-221), or LFIntegrator.reverse for the generate config (main.py:269).
+    Falls back to the CPU port of the same algorithm (oracle/, kind 'port') when baseline/_ref is absent.
+    Returns (molecules/s, threads, seconds per step, kind)."""
     torch.set_num_threads(os.cpu_count())
     arrs = syn.make_batch(config, sample_mols, **kwargs)
     sd = syn.make_weights(nf, H, L_LAYERS, seed=0, coord_gain=0.5)
     eps = syn.make_noise(int(arrs['N'].sum()), nf)
+    mods = _import_reference()
+    if mods is None:
+        from oracle import enflow_oracle as orc
+
+        def one():
+            if config == 'c4':
+                with torch.no_grad():
+                    orc.lf_reverse(orc.params_to_torch(sd), L_LAYERS, orc.to_torch(arrs), syn.TRAIN_DT)
+            else:
+                orc.train_step(sd, L_LAYERS, arrs, syn.TRAIN_DT, eps, syn.TRAIN_KBT, syn.TRAIN_SOFTENING)
+        kind = 'port'
+    else:
+        rbase, regcl, rargmax, rdyn, rloss = mods
+        model = rdyn.LFIntegrator([regcl.EGCL(nf, nf, H) for _ in range(L_LAYERS)], rargmax.ArgMax(nf, H), dt=syn.TRAIN_DT)
+        model.load_state_dict({k: torch.tensor(v, dtype=torch.float64) for k, v in sd.items()})
+        nll = rloss.Alchemical_NLL(kBT=syn.TRAIN_KBT, softening=syn.TRAIN_SOFTENING)
+
+        def batch():
+            mols, o = [], 0
+            for m, n in enumerate(arrs['N']):
+                n = int(n)
+                sl = slice(o, o + n)
+                mols.append(rbase.Data(z=['X'] * n, h=torch.tensor(arrs['h'][sl]), g=torch.tensor(arrs['g'][sl]),
+                                       pos=torch.tensor(arrs['pos'][sl]), vel=torch.tensor(arrs['vel'][sl]), N=n,
+                                       r_cut=float(arrs['r_cut'][m]), box=torch.tensor(arrs['box'][sl]), label=[0] * n))
+                o += n
+            return rbase.DataLoader.collater(None, mols)      # an ordinary method that does not touch self
+
+        def one():
+            data = batch()
+            if config == 'c4':
+                with torch.no_grad():
+                    model.reverse(data)
+            else:
+                model.zero_grad(set_to_none=True)
+                out, ldj = model(data)
+                nll(out, ldj).backward()
+        kind = 'reference'
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        if config == 'c4':
-            with torch.no_grad():
-                orc.lf_reverse(orc.params_to_torch(sd), L_LAYERS, orc.to_torch(arrs), syn.TRAIN_DT)
-        else:
-            orc.train_step(sd, L_LAYERS, arrs, syn.TRAIN_DT, eps, syn.TRAIN_KBT, syn.TRAIN_SOFTENING)
+        one()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return sample_mols / (sum(times) / len(times)), torch.get_num_threads(), sum(times) / len(times)
+    sec = sum(times) / len(times)
+    return sample_mols / sec, torch.get_num_threads(), sec, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host CPU (the reference is pure Python/PyTorch and cannot
-    travel to the GPU box, so the port under oracle/ - pinned against the unmodified reference by tests/golden - stands
-    in: kind 'port').  Same config / steps / warmup as the b200 arm; each step is a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores: the unmodified tree vendored
+    to baseline/_ref by build() (kind 'reference'); the port under oracle/ (pinned against it by tests/golden) only if that
+    tree is absent (kind 'port').  Same config / steps / warmup as the b200 arm; each step is a bounded sample."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
@@ -178,13 +234,13 @@ def run_reference(args):
     n_mol = int(arrs['N'][0])
     n_atoms = n_mol * batch
     E = n_mol * (n_mol - 1) * batch if config in ('c2', 'c3') else None      # radius-graph configs: data dependent
-    mols_s, cores, sec = cpu_port_throughput(config, nf, sample, args.steps, args.warmup, kwargs)
+    mols_s, cores, sec, kind = cpu_reference_throughput(config, nf, sample, args.steps, args.warmup, kwargs)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': mols_s, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(config, batch, world, nf, desc, n_atoms, E),
-        'cpu_baseline': {'value': mols_s, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'cpu_baseline': {'value': mols_s, 'unit': UNIT, 'cores': cores, 'kind': kind,
                          'sample': f'{sample} molecules of the same config per step (per-molecule throughput), fp64 torch CPU, '
                                    f'all host threads; {args.warmup} warm-up + {args.steps} timed steps'},
         'e2e': {'value': mols_s, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -455,10 +511,11 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c4': 256, 'c5': 1}[args.config]
-            mols_s, cores, sec = cpu_port_throughput(config, nf, sample, 2, 1, kwargs)
-            line['cpu_baseline'] = {'value': mols_s, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': f'{sample} molecules of the same config per step, fp64 torch CPU port '
-                                              f'of the reference algorithm (oracle/), 1 warm-up + 2 timed steps'}
+            mols_s, cores, sec, kind = cpu_reference_throughput(config, nf, sample, 2, 1, kwargs)
+            line['cpu_baseline'] = {'value': mols_s, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                    'sample': f'{sample} molecules of the same config per step, fp64 torch CPU, '
+                                              + ('the unmodified reference (baseline/_ref)' if kind == 'reference' else
+                                                 'port of the reference algorithm (oracle/)') + ', 1 warm-up + 2 timed steps'}
         print(json.dumps(line), flush=True)
     if world > 1:
         # tear down: the graphs that captured the gradient all-reduce go first (destroying an NCCL communicator while a

@@ -358,8 +358,8 @@ int enf_tc_pack_layers(const float* lp0, int nf, int L, int64_t param_stride, un
 }
 
 int enf_edge_fwd_tc_v2(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
-                       const float* box, const float* P, const float* S, const float* lp, int nf, const int* rowptr,
-                       const int* mis, float* runs, float* s_out, float* trans, cudaStream_t st);
+                       const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg, int nf,
+                       const int* rowptr, const int* mis, float* runs, float* s_out, float* trans, cudaStream_t st);
 
 // mode 1 = split (fp32-accurate), mode 2 = bf16.  The product kernel is edge_tc_fwd.cu (weights in TMEM, two tiles in
 // flight); ENFLOW_FWD_V1=1 selects the round-1 kernel above for A/B timing.
@@ -369,7 +369,7 @@ int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, 
                     cudaStream_t st) {
     if (E_cap == 0) return ENF_OK;
     static const bool v1 = getenv("ENFLOW_FWD_V1") != nullptr;
-    if (!v1) return enf_edge_fwd_tc_v2(mode, row, col, E_dev, E_cap, pos, box, P, S, lp, nf, rowptr, mis, runs, s_out, trans, st);
+    if (!v1) return enf_edge_fwd_tc_v2(mode, row, col, E_dev, E_cap, pos, box, P, S, lp, wimg, nf, rowptr, mis, runs, s_out, trans, st);
     const EgclOffsets o = enf_egcl_offsets(nf);
     int grid = (E_cap + tc::TILE - 1) / tc::TILE;
     if (grid > enf_num_sms()) grid = enf_num_sms();

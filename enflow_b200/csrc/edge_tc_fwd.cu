@@ -8,7 +8,7 @@
 // (128 KB, fp32-accurate mode) in shared memory, which left room for ONE activation buffer, so a tile's second GEMM
 // ran in front of an idle CTA and nothing was above 50 % busy (issue 50 %, XU 46 %, L1 data pipe 57 %, tensor 23 %).
 // Here the weights are the A operand read from TENSOR MEMORY (tcgen05.mma with A in TMEM): thread (hidden unit n)
-// writes row n of W2 / W3 as packed bf16 (hi and lo images, 64 columns each) with tcgen05.st once per CTA.  That
+// moves row n of the packed bf16 images of W2 / W3 (hi and lo, 64 columns each) into TMEM with tcgen05.st once per CTA.  That
 //   * frees 128 KB of shared memory: two 64 KB activation buffers, i.e. two 128-edge tiles in flight at N = 128;
 //   * halves the MMA operand traffic on the L1 data pipe (only the 4 KB activation slice is read per MMA);
 //   * keeps the transposed accumulator (TMEM lane = hidden unit, column = edge) the reductions over edges need.
@@ -112,8 +112,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ E_dev, int E_cap,
               const float* __restrict__ pos, const float* __restrict__ box, const float* __restrict__ P,
-              const float* __restrict__ S, const float* __restrict__ W1, int e1, const float* __restrict__ W2,
-              const float* __restrict__ W3, const float* __restrict__ b2, const float* __restrict__ b3,
+              const float* __restrict__ S, const float* __restrict__ W1, int e1,
+              const unsigned char* __restrict__ wimg, const float* __restrict__ b2, const float* __restrict__ b3,
               const float* __restrict__ wc, const int* __restrict__ rowptr, const int* __restrict__ mis,
               float* __restrict__ runs, float* __restrict__ s_out, float* __restrict__ trans) {
     using L = SmemF<SPLIT>;
@@ -127,11 +127,13 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     uint64_t* bar_opnd = bars + 2;             // [2] operand image of pipeline p is written, T read (epilogue -> MMA)
     uint64_t* bar_full = bars + 4;             // [RING] tile record written                          (geometry -> epilogue)
     uint64_t* bar_empty = bars + 4 + RING;     // [RING] tile record no longer read                   (epilogue -> geometry)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * RING);
+    uint64_t* bar_w = bars + 4 + 2 * RING;      // weight images have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * RING);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     if (tid == 0) {
+        tc::mbar_init(bar_w, 1);
         for (int p = 0; p < 2; ++p) {
             tc::mbar_init(bar_acc + p, 1);
             tc::mbar_init(bar_opnd + p, EPI_THREADS / 32);
@@ -154,28 +156,31 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
     const int G = gridDim.x, cta = blockIdx.x;
     const int T = cta < tiles ? (tiles - cta + G - 1) / G : 0;          // this CTA's tiles: cta, cta + G, ...
 
-    // ---- weights -> TMEM (A operand): thread n writes row n of W2 / W3 as packed bf16, 64 columns per image
-    if (w < 16) {
-        const int q = w & 3, img = w >> 2;                     // split: W2 hi, W2 lo, W3 hi, W3 lo; bf16: W2, W3
-        if (SPLIT || img < 2) {
-            const int n = 32 * q + lane;
-            const float* Wsrc = ((SPLIT ? (img >> 1) : img) ? W3 : W2) + (int64_t)n * ENF_H;
-            const bool want_lo = SPLIT && (img & 1);
-            const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + W_COL + 64u * img;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {                      // 32 input features = 16 packed words
-                float v[16];
+    // ---- weights -> TMEM (A operand).  The packed bf16 images (k_pack_tc: W2 hi, W2 lo, W3 hi, W3 lo, each [n][k] in the
+    //      swizzled operand layout) are staged through the still unused activation buffers by TMA bulk copies; thread n
+    //      then moves row n of one image (256 B = 64 packed words) into 64 TMEM columns with tcgen05.st.
+    constexpr int NW = SPLIT ? 4 : 2;
+    if (tid == 0) {
+        tc::mbar_expect_tx(bar_w, NW * tc::IMG_BYTES);
+        for (int i = 0; i < NW; ++i)
+            tc::bulk_g2s(XB + (size_t)i * tc::IMG_BYTES, wimg + (size_t)(SPLIT ? i : 2 * i) * tc::IMG_BYTES, tc::IMG_BYTES, bar_w);
+    }
+    if (w < 4 * NW) {
+        const int q = w & 3, img = w >> 2;
+        const int n = 32 * q + lane;
+        tc::mbar_wait(bar_w, 0);
+        const unsigned char* src = XB + (size_t)img * tc::IMG_BYTES;
+        const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + W_COL + 64u * img;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(Wsrc + 32 * c) + j);
-                    uint32_t h0, l0, h1, l1;
-                    tc::split2(x.x, x.y, h0, l0);
-                    tc::split2(x.z, x.w, h1, l1);
-                    v[2 * j] = __uint_as_float(want_lo ? l0 : h0);
-                    v[2 * j + 1] = __uint_as_float(want_lo ? l1 : h1);
-                }
-                tc::tmem_st16(dst + 16u * c, v);
+        for (int c = 0; c < 4; ++c) {                      // 32 input features = 4 chunks of 16 bytes = 16 packed words
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 x = *reinterpret_cast<const uint4*>(src + tc::img_chunk_offset(n, 4 * c + j));
+                v[4 * j] = __uint_as_float(x.x); v[4 * j + 1] = __uint_as_float(x.y);
+                v[4 * j + 2] = __uint_as_float(x.z); v[4 * j + 3] = __uint_as_float(x.w);
             }
+            tc::tmem_st16(dst + 16u * c, v);
         }
     }
     tc::fence_before_sync();
@@ -420,8 +425,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 }  // namespace
 
 int enf_edge_fwd_tc_v2(int mode, const int* row, const int* col, const int* E_dev, int E_cap, const float* pos,
-                       const float* box, const float* P, const float* S, const float* lp, int nf, const int* rowptr,
-                       const int* mis, float* runs, float* s_out, float* trans, cudaStream_t st) {
+                       const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg, int nf,
+                       const int* rowptr, const int* mis, float* runs, float* s_out, float* trans, cudaStream_t st) {
     if (E_cap == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     int grid = (E_cap + TE - 1) / TE;
@@ -434,11 +439,11 @@ int enf_edge_fwd_tc_v2(int mode, const int* row, const int* col, const int* E_de
     }
     if (mode == 1)
         enf_count_launch(), k_edge_fwd_tc<true><<<grid, THREADS, SmemF<true>::total, st>>>(
-            row, col, E_dev, E_cap, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_W2], lp + o.off[P_W3],
+            row, col, E_dev, E_cap, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, wimg,
             lp + o.off[P_B2], lp + o.off[P_B3], lp + o.off[P_WC], rowptr, mis, runs, s_out, trans);
     else
         enf_count_launch(), k_edge_fwd_tc<false><<<grid, THREADS, SmemF<false>::total, st>>>(
-            row, col, E_dev, E_cap, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, lp + o.off[P_W2], lp + o.off[P_W3],
+            row, col, E_dev, E_cap, pos, box, P, S, lp + o.off[P_W1], 2 * nf + 1, wimg,
             lp + o.off[P_B2], lp + o.off[P_B3], lp + o.off[P_WC], rowptr, mis, runs, s_out, trans);
     ENF_CHECK_LAUNCH();
     return ENF_OK;

@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(256) k_segment_sum128(const float* __restrict_
                                                          float scale3, float* __restrict__ out3) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps_per_grid) {
+    for (int ii = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ii < N; ii += warps_per_grid) {
+        // Segments are walked from the LAST one: `x` was written front to back by the kernel before this one and is
+        // larger than the L2 (E*H*4 = 426 MB on C2), so its tail is what is still resident when this kernel starts.
+        const int i = N - 1 - ii;
         int e0 = ptr[i], e1 = ptr[i + 1];
         if (e1 > E_cap) e1 = E_cap;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);

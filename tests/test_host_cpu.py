@@ -80,3 +80,18 @@ def test_no_cpu_fallback():
     data = batch_from_arrays(syn.make_batch('c2', 1, n_atoms=4))
     with pytest.raises(RuntimeError, match='CUDA'):
         m(data)
+
+
+def test_bench_reference_arm_runs_the_vendored_reference():
+    """`bench.py --impl reference` / the cpu_baseline leg: the unmodified reference from baseline/_ref when build() vendored
+    it (kind 'reference'), else the port under oracle/ (kind 'port'); both give a finite molecules/s on a tiny sample."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    mols_s, cores, sec, kind = bench.cpu_reference_throughput('c2', 5, 2, 1, 0, {'n_atoms': 6})
+    vendored = os.path.exists(os.path.join(root, 'baseline', '_ref', 'enflow', 'flow', 'dynamics.py'))
+    assert kind == ('reference' if vendored else 'port')
+    assert mols_s > 0 and cores >= 1 and sec > 0
