@@ -62,6 +62,7 @@ SIGNATURES = {
     'enflow_coupling_inv_pre': (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp]),
     'enflow_coupling_inv_post': (i32, [vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]),
     'enflow_argmax_fwd': (i32, [vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'enflow_nll_slices': (i32, [i32]),
     'enflow_nll_fwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
     'enflow_nll_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
     'enflow_flow_workspace_bytes': (sz, [C.POINTER(Dims), i32]),

@@ -223,6 +223,8 @@ int enflow_argmax_fwd(const float* h, const float* eps, int N, int nf, const flo
     return enf_argmax_fwd(h, eps, N, nf, ap, mol_off, B, z, logq_atom, logq_mol, log_q, ST(stream));
 }
 
+int enflow_nll_slices(int max_n) { return enf_nll_slices(max_n); }
+
 int enflow_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B,
                    int N, int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj,
                    double* mol_term, float* loss, void* stream) {

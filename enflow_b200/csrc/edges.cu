@@ -368,92 +368,61 @@ __global__ void k_col_count(const int* __restrict__ col, const int* __restrict__
         atomicAdd(&colcnt[col[e]], 1);       // integer adds: the result does not depend on order
 }
 
-// one CTA per molecule; chunks of 256 edges; rank among equal columns by comparison in smem
-__global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, const int* __restrict__ rowptr,
-                                                   const int* __restrict__ mol_off, const int* __restrict__ colptr,
-                                                   int* __restrict__ cursor, int* __restrict__ perm, int E_cap,
-                                                   const int* __restrict__ skip) {
+// Fill: every edge takes the next free slot of its column (integer atomics: WHICH slot is order dependent, the set of
+// edges of a column is not), then k_col_sort puts every column's list into increasing edge order.  The result is the
+// stable column-grouped permutation whatever order the atomics ran in: deterministic.
+__global__ void __launch_bounds__(256) k_col_fill(const int* __restrict__ col, const int* __restrict__ E_dev,
+                                                   const int* __restrict__ colptr, int* __restrict__ cursor,
+                                                   int* __restrict__ perm, const int* __restrict__ skip) {
     if (skip && *skip) return;
-    __shared__ int ccol[256];
-    const int m = blockIdx.x;
-    const int e_begin = rowptr[mol_off[m]];
-    int e_end = rowptr[mol_off[m + 1]];
-    if (e_end > E_cap) e_end = E_cap;
-    for (int e0 = e_begin; e0 < e_end; e0 += 256) {
-        const int e = e0 + threadIdx.x;
-        const int c = e < e_end ? col[e] : -1;
-        ccol[threadIdx.x] = c;
-        __syncthreads();
-        int before = 0, after = 0;
-        if (c >= 0) {
-            for (int t = 0; t < 256; ++t) {
-                const bool same = ccol[t] == c;
-                before += (same && t < threadIdx.x);
-                after += (same && t > threadIdx.x);
-            }
-            perm[colptr[c] + cursor[c] + before] = e;
-        }
-        __syncthreads();
-        if (c >= 0 && after == 0) cursor[c] += before + 1;   // exactly one thread per distinct column
-        __syncthreads();
+    const int E = E_dev[0];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int c = col[e];
+        perm[colptr[c] + atomicAdd(&cursor[c], 1)] = e;
     }
 }
 
-// Large molecules: one warp per group of 32 consecutive columns (lane <-> column) scans the edges of the molecules
-// those columns belong to once (coalesced, eight loads in flight) and appends every match to its column's list in
-// edge order: lanes holding the same column are ranked with match.any, the per-column write positions live in
-// shared memory.  Stable, no serial chunk loop, no atomics.
-__global__ void __launch_bounds__(256) k_col_fill_warp(const int* __restrict__ col, const int* __restrict__ rowptr,
-                                                        const int* __restrict__ mol_off, int B, int N,
-                                                        const int* __restrict__ colptr, int* __restrict__ perm,
-                                                        int E_cap, const int* __restrict__ skip) {
+// one warp per column: rank sort of its (distinct) edge ids held in registers, up to 32 * KMAX entries; longer lists are
+// sorted in place by one lane (a column with more than 256 incoming edges: not seen in any config)
+__global__ void __launch_bounds__(256) k_col_sort(const int* __restrict__ colptr, int N, int* __restrict__ perm,
+                                                   const int* __restrict__ skip) {
     if (skip && *skip) return;
-    __shared__ int pos_s[8][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * 8 + wid;
-    const int c0 = 32 * g;
-    if (c0 >= N) return;
-    int* pos = pos_s[wid];
-    pos[lane] = c0 + lane < N ? colptr[c0 + lane] : 0;
-    // edge range: from the molecule of the first column to the molecule of the last one
-    const int cl = lane == 0 ? c0 : min(c0 + 31, N - 1);
-    int lo = 0, hi = B;                                     // mol_off[lo] <= cl < mol_off[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (mol_off[mid] <= cl) lo = mid; else hi = mid;
-    }
-    const int m_lo = __shfl_sync(0xffffffffu, lo, 0), m_hi = __shfl_sync(0xffffffffu, lo, 31);
-    const int e_lo = rowptr[mol_off[m_lo]];
-    int e_hi = rowptr[mol_off[m_hi + 1]];
-    if (e_hi > E_cap) e_hi = E_cap;
-    __syncwarp();
-    const unsigned lt = (1u << lane) - 1u;
-    for (int e0 = e_lo; e0 < e_hi; e0 += 256) {
-        int cv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + 32 * u + lane;
-            cv[u] = e < e_hi ? col[e] : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = e0 + 32 * u + lane;
-            const int lc = cv[u] - c0;
-            const bool mine = (unsigned)lc < 32u;
-            const unsigned act = __ballot_sync(0xffffffffu, mine);
-            if (act == 0) continue;
-            unsigned same = 0;
-            int base = 0;
-            if (mine) {
-                same = __match_any_sync(act, lc);
-                base = pos[lc];
-                perm[base + __popc(same & lt)] = e;
+    constexpr int KMAX = 8;
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= N) return;
+    const int s0 = colptr[c], d = colptr[c + 1] - s0;
+    if (d <= 1) return;
+    if (d > 32 * KMAX) {
+        if (lane == 0)
+            for (int i = 1; i < d; ++i) {
+                const int v = perm[s0 + i];
+                int j = i - 1;
+                while (j >= 0 && perm[s0 + j] > v) { perm[s0 + j + 1] = perm[s0 + j]; --j; }
+                perm[s0 + j + 1] = v;
             }
-            __syncwarp();
-            if (mine && (same & lt) == 0) pos[lc] = base + __popc(same);     // one leader per column
-            __syncwarp();
+        return;
+    }
+    const int K = (d + 31) >> 5;                 // warp-uniform
+    int v[KMAX], rank[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        v[k] = (k < K && lane + 32 * k < d) ? perm[s0 + lane + 32 * k] : 0x7fffffff;
+        rank[k] = 0;
+    }
+#pragma unroll
+    for (int kj = 0; kj < KMAX; ++kj) {
+        if (kj >= K) break;
+        for (int src = 0; src < 32; ++src) {
+            const int wv = __shfl_sync(0xffffffffu, v[kj], src);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) rank[k] += wv < v[k];
         }
     }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < K && lane + 32 * k < d) perm[s0 + rank[k]] = v[k];
 }
 
 __global__ void k_zero_int2(int* __restrict__ p, int64_t n, int* __restrict__ q, int64_t m, const int* __restrict__ skip) {
@@ -630,11 +599,8 @@ int enf_build_col_perm(const int* col, const int* rowptr, const int* mol_off, in
     enf_count_launch(), k_col_count<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr, skip);
     ENF_CHECK_LAUNCH();
     ENF_TRY(scan2(colptr, nullptr, N, sums, st, skip));
-    if (N <= 96LL * B)
-        enf_count_launch(), k_col_fill<<<B, 256, 0, st>>>(col, rowptr, mol_off, colptr, cursor, perm, E_cap, skip);
-    else        // large molecules: a CTA per molecule would leave the GPU empty
-        enf_count_launch(), k_col_fill_warp<<<((N + 31) / 32 + 7) / 8, 256, 0, st>>>(col, rowptr, mol_off, B, N, colptr, perm,
-                                                                                     E_cap, skip);
+    enf_count_launch(), k_col_fill<<<enf_num_sms() * 4, 256, 0, st>>>(col, E_dev, colptr, cursor, perm, skip);
+    enf_count_launch(), k_col_sort<<<(N + 7) / 8, 256, 0, st>>>(colptr, N, perm, skip);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

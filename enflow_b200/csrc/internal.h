@@ -61,6 +61,7 @@ int enf_argmax_bwd(const float* h, const float* eps, int N, int nf, const float*
                    const float* dlogq, float* agrad, float* partial, cudaStream_t st);
 int enf_argmax_reverse(float* h, int N, int nf, cudaStream_t st);
 
+int enf_nll_slices(int max_n);
 int enf_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int* mol_off, int B, int N,
                 int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj, double* mol_term,
                 float* loss, cudaStream_t st);

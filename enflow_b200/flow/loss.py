@@ -12,7 +12,7 @@ class _NLLFn(torch.autograd.Function):
         N, nf = int(pos.shape[0]), int(h.shape[1])
         pos, vel, h, g = (_lib.f32c(t) for t in (pos, vel, h, g))
         ldj1 = _lib.f32c(ldj).reshape(1)
-        mol_term = torch.empty(B, dtype=torch.float64, device=dev)
+        mol_term = torch.empty(B * int(L.enflow_nll_slices(max_n)), dtype=torch.float64, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         p = _lib.ptr
         _lib.check(L.enflow_nll_fwd(p(pos), p(vel), p(h), p(g), p(off), B, N, nf, max_n, kBT, softening, z_lj,

@@ -153,7 +153,10 @@ int enflow_argmax_fwd(const float* h, const float* eps, int N, int nf, const flo
                       const int32_t* mol_off, int B, float* z, float* logq_atom, double* logq_mol, float* log_q,
                       void* stream);
 
-/* ---- K5 likelihood: Alchemical_NLL (enflow/flow/loss.py:11-25) -------------------------------- */
+/* ---- K5 likelihood: Alchemical_NLL (enflow/flow/loss.py:11-25) --------------------------------
+ * A molecule is evaluated in slices of 128 atoms (one CTA each): `mol_term` is caller-provided scratch of
+ * B * enflow_nll_slices(max_n) doubles (one partial per molecule and slice, added in index order). */
+int enflow_nll_slices(int max_n);
 int enflow_nll_fwd(const float* pos, const float* vel, const float* h, const float* g, const int32_t* mol_off, int B,
                    int N, int nf, int max_n, float kBT, float softening, float z_lj, const float* ldj,
                    double* mol_term, float* loss, void* stream);

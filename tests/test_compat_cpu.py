@@ -29,5 +29,5 @@ def test_bench_reference_arm_runs_on_cpu():
                           '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line['impl'] == 'reference' and line['cpu_baseline']['kind'] == 'port' and line['value'] > 0
+    assert line['impl'] == 'reference' and line['cpu_baseline']['kind'] in ('reference', 'port') and line['value'] > 0
     assert line['e2e']['h2d_bytes_per_step'] == 0

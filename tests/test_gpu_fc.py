@@ -149,3 +149,20 @@ def test_wrong_fc_assumption_falls_back_to_k0():
     for k in ('h', 'g', 'pos', 'vel'):
         err = np.abs(to_np(getattr(out, k)) - c['gold'][f'out_{k}']).max() / np.abs(c['gold'][f'out_{k}']).max()
         assert err < 1e-5, k
+
+
+@pytest.mark.parametrize('name', ['c1_pbc', 'c5_small', 'c5_radius', 'c2_ragged'])
+def test_col_perm_is_the_stable_column_grouping(name):
+    """enflow_build_col_perm on radius-graph lists (duplicate (row, col) pairs from periodic images included, Q11): the
+    column-grouped permutation equals numpy's stable argsort of col, twice in a row (the slots are handed out by integer
+    atomics and each column's list is sorted afterwards, so the result must not depend on their order)."""
+    c = load_case(name)
+    data = gpu_batch(c['batch'], dtype=torch.float32)
+    e = data.build_edges(reference_order=False)
+    col = e.csr[1].cpu().numpy().astype(np.int64)
+    ref = np.argsort(col, kind='stable').astype(np.int64)
+    for _ in range(2):
+        colptr, perm = _k0_col_perm(data, e.csr)
+        assert np.array_equal(perm.cpu().numpy().astype(np.int64), ref)
+        counts = np.bincount(col, minlength=int(data.pos.shape[0]))
+        assert np.array_equal(np.diff(colptr.cpu().numpy().astype(np.int64)), counts)

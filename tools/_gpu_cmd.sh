@@ -1,10 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for c in c2 c1; do
-  timeout 300 python bench.py --config $c --steps 10 --no-cpu-baseline > gpurun_out/r2e_bench_$c.json 2> gpurun_out/r2e_bench_$c.err; echo "bench $c rc=$?"
-done
-python - <<'PY'
-import json
-for c in ('c2','c1'):
-    d=json.load(open(f'gpurun_out/r2e_bench_{c}.json'))
-    print(c, round(d['value']), round(d['ms_per_step'],3), {k: round(v,3) for k,v in d['kernel_ms_per_step'].items() if k.startswith('edge')})
-PY
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
