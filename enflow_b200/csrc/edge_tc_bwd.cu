@@ -243,8 +243,11 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
 
     const int E = E_dev[0] < E_cap ? E_dev[0] : E_cap;
     const int tiles = (E + TE - 1) / TE;
-    const int G = gridDim.x, cta = blockIdx.x;
-    const int T = cta < tiles ? (tiles - cta + G - 1) / G : 0;          // this CTA's tiles: cta, cta + G, ...
+    // this CTA's tiles: tile0 .. tile0 + T - 1.  A contiguous range keeps a molecule's rows of P / S / dagg in this SM's L1
+    // from tile to tile (measured 3.41 -> 3.38 ms per step on C2 against the strided assignment)
+    const int Tc = (tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile0 = blockIdx.x * Tc;
+    const int T = tiles - tile0 < 0 ? 0 : (tiles - tile0 < Tc ? tiles - tile0 : Tc);
     const int periods = (T + 2) / 2;                                     // k = 0 .. while 2k - 1 < T
 
     if (w >= 16) {
@@ -265,7 +268,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
             if (lane == 0) {
                 const int s = t % RING;
                 tc::mbar_expect_tx(bar_idx + s, IDX_BYTES);
-                tc::bulk_g2s(ring + s * IDX_INTS, gv.idx + (int64_t)(cta + t * G) * IDX_INTS, IDX_BYTES, bar_idx + s);
+                tc::bulk_g2s(ring + s * IDX_INTS, gv.idx + (int64_t)(tile0 + t) * IDX_INTS, IDX_BYTES, bar_idx + s);
             }
         };
         // wait for the epilogue warps' arrivals on pipeline p, then the whole warp runs `body` (one elected lane issues)
@@ -364,7 +367,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
             wait_bar(bar_idx + s, (uint32_t)(t / RING) & 1);
             const int* ir = ring + s * IDX_INTS + ec;
             const int bits = ring[s * IDX_INTS + 2 * TE + 2 * cg + 1];
-            const float4* r4 = reinterpret_cast<const float4*>(gv.r + (int64_t)(cta + t * G) * TE + ec);
+            const float4* r4 = reinterpret_cast<const float4*>(gv.r + (int64_t)(tile0 + t) * TE + ec);
             // requests first (every load has its own destination register), the repeats are filled in afterwards
             float pz[16];
 #pragma unroll
@@ -448,7 +451,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
         // ---- E2(t): z3 -> dz3^T image; t_prev_other >= 0: tile of the other pipeline whose G4 still reads the shared buffer
         auto taskE2 = [&](auto PP, int t, int tg, float (&sg_other)[16]) {
             constexpr int p = decltype(PP)::value;
-            const float4* d4 = reinterpret_cast<const float4*>(gv.ds + (int64_t)(cta + t * G) * TE + ec);
+            const float4* d4 = reinterpret_cast<const float4*>(gv.ds + (int64_t)(tile0 + t) * TE + ec);
             float dsv[16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -484,7 +487,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
         // ---- E3(t): dx2 -> dz2^T image, x1^T image rebuilt (x2^T is dead), silu'(z1) kept
         auto taskE3 = [&](auto PP, int t, float (&st)[16]) {
             constexpr int p = decltype(PP)::value;
-            const int e0 = (cta + t * G) * TE;
+            const int e0 = (tile0 + t) * TE;
             const int* ir = ring + (t % RING) * IDX_INTS + ec;
             const int bits = ring[(t % RING) * IDX_INTS + 2 * TE + 2 * cg + 1];
             float pf[16];                               // dagg rows: requested where the row changes, repeats filled in below
@@ -531,7 +534,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
             constexpr int p = decltype(PP)::value;
             const bool has_t = t >= 0 && t < T, has_x = t2 < T;
             if (has_t) {
-                const int tile = cta + t * G;
+                const int tile = tile0 + t;
                 const int e0 = tile * TE;
                 const int2 hdr = __ldg(gv.hdr + (int64_t)tile * 4 + cg);
                 const float4* r4 = reinterpret_cast<const float4*>(gv.r + (int64_t)e0 + ec);

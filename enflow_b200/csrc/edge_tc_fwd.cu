@@ -153,8 +153,10 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 
     const int E = E_dev[0] < E_cap ? E_dev[0] : E_cap;
     const int tiles = (E + TE - 1) / TE;
-    const int G = gridDim.x, cta = blockIdx.x;
-    const int T = cta < tiles ? (tiles - cta + G - 1) / G : 0;          // this CTA's tiles: cta, cta + G, ...
+    // this CTA's tiles: tile0 .. tile0 + T - 1 (a contiguous range keeps a molecule's rows of P / S in this SM's L1)
+    const int Tc = (tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile0 = blockIdx.x * Tc;
+    const int T = tiles - tile0 < 0 ? 0 : (tiles - tile0 < Tc ? tiles - tile0 : Tc);
 
     // ---- weights -> TMEM (A operand).  The packed bf16 images (k_pack_tc: W2 hi, W2 lo, W3 hi, W3 lo, each [n][k] in the
     //      swizzled operand layout) are staged through the still unused activation buffers by TMA bulk copies; thread n
@@ -226,7 +228,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
                 if (t >= RING) tc::mbar_wait(bar_empty + slot, (uint32_t)(t / RING - 1) & 1);
                 TileRec& tr = rec[slot];
                 const int m = 32 * g + lane;
-                const int e = (cta + t * G) * TE + m;
+                const int e = (tile0 + t) * TE + m;
                 const bool ok = e < E;
                 int i = 0, j = 0, start = 0, mi = 0;
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f;
@@ -332,7 +334,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
         auto taskE1 = [&](auto PP, int t) {
             constexpr int p = decltype(PP)::value;
             const TileRec& tr = rec[t % RING];
-            const int e0 = (cta + t * G) * TE;
+            const int e0 = (tile0 + t) * TE;
             const int2 hd[2] = {tr.hdr[2 * cg], tr.hdr[2 * cg + 1]};
             wait_acc(p, 0);
             float v[32];
@@ -391,7 +393,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
             if (has_t) {
                 const int slot = t % RING;
                 const TileRec& tr = rec[slot];
-                const int e0 = (cta + t * G) * TE;
+                const int e0 = (tile0 + t) * TE;
                 tc::named_bar_sync(1 + cg, 128);                   // the four quarter-warps of this edge group
                 if (lane < 24) {
                     const int el = ec + 8 * q + lane / 3, c = lane % 3;
