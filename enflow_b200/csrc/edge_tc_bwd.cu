@@ -404,7 +404,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float z = z1[8 * ch + j];
-                    const float sg = tc::sigmoid_sfu(z);
+                    const float sg = tc::sigmoid_t<SPLIT>(z);
                     x[j] = z * sg;
                     if (decltype(DS)::value) z1[8 * ch + j] = fmaf(x[j], 1.0f - sg, sg);       // silu'(z) = s + z s (1 - s)
                 }
@@ -439,7 +439,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
                 for (int j = 0; j < 8; ++j) {
                     const int jj = 8 * ch + j;
                     const float z = v[jj] + b2n;
-                    const float sg = tc::sigmoid_sfu(z);
+                    const float sg = tc::sigmoid_t<SPLIT>(z);
                     x[j] = z * sg;
                     v[jj] = fmaf(x[j], 1.0f - sg, sg);
                 }
@@ -464,7 +464,7 @@ k_edge_bwd_tc(GeomView gv, const int* __restrict__ E_dev, int E_cap,
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const float z = v[jj] + b3n;
-                const float sg = tc::sigmoid_sfu(z);
+                const float sg = tc::sigmoid_t<SPLIT>(z);
                 const float ds = dsv[jj];
                 const float x3 = z * sg;
                 gwc = fmaf(ds, x3, gwc);

@@ -314,8 +314,8 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int m = 8 * w + it;
-                const float x0 = z[it].x * tc::sigmoid_sfu(z[it].x), x1 = z[it].y * tc::sigmoid_sfu(z[it].y);
-                const float x2 = z[it].z * tc::sigmoid_sfu(z[it].z), x3 = z[it].w * tc::sigmoid_sfu(z[it].w);
+                const float x0 = z[it].x * tc::sigmoid_t<SPLIT>(z[it].x), x1 = z[it].y * tc::sigmoid_t<SPLIT>(z[it].y);
+                const float x2 = z[it].z * tc::sigmoid_t<SPLIT>(z[it].z), x3 = z[it].w * tc::sigmoid_t<SPLIT>(z[it].w);
                 const uint32_t off = tc::img_chunk_offset(m, lane >> 1) + ((lane & 1) << 3);
                 if (SPLIT) {
                     uint2 hi, lo;
@@ -342,7 +342,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float z = v[j] + b2n;
-                v[j] = z * tc::sigmoid_sfu(z);
+                v[j] = z * tc::sigmoid_t<SPLIT>(z);
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -378,7 +378,7 @@ k_edge_fwd_tc(const int* __restrict__ row, const int* __restrict__ col, const in
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float y = v[j] + b3n;
-                        v[j] = wcn * (y * tc::sigmoid_sfu(y));
+                        v[j] = wcn * (y * tc::sigmoid_t<SPLIT>(y));
                     }
                     const float tsum = tc::warp_transpose_sum16(v, lane);
                     if (!(lane & 1)) sp[q * TE + ec + 16 * half + (lane >> 1)] = tsum;

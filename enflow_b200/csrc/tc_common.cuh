@@ -257,6 +257,17 @@ __device__ __forceinline__ float sigmoid_sfu(float x) {
 }
 
 
+// sigmoid of the edge kernels: ACCURATE (fp32-accurate mode) = the two-MUFU form above; otherwise 0.5 + 0.5 tanh(x / 2) with
+// one MUFU (tanh.approx: 2^-11 relative), well inside what bf16 operands (2^-9) leave of the 1e-2 budget of bf16 mode.
+// The forward kernel is bound by the SFU (three sigmoid passes per element), so this is a third of its time in that mode.
+template <bool ACCURATE>
+__device__ __forceinline__ float sigmoid_t(float x) {
+    if (ACCURATE) return sigmoid_sfu(x);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+
 // ---- per-thread helpers of the edge-kernel epilogues ---------------------------------------------------------
 // sum over the 32 lanes of 16 per-lane values by recursive halving (16 shuffles): lane l receives column (l >> 1)
 __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
