@@ -465,8 +465,10 @@ def main():
                              f'The tensor pipe executes {mma_per_gemm} bf16 MMA(s) per GEMM term (the bf16x3 operand split keeps '
                              f'fp32 parity) and {gemms} GEMMs per tile'
                              + (' (2 recompute + 2 dgrad + 2 wgrad)' if dom == 'edge_bwd' else '')
-                             + '; pipe_tensor_active_pct is what ncu measured for the executed MMAs. The kernel is bound by the '
-                               'L1/shared-memory data pipe (MMA operand reads + epilogue traffic), DESIGN.md section 4') if tc_mode
+                             + '; pipe_tensor_active_pct is what ncu measured for the executed MMAs. '
+                             + ('The kernel is bound by the L1/shared-memory data pipe (MMA operand reads + epilogue traffic)'
+                                if dom == 'edge_bwd' else 'The kernel is bound by the SFU (three sigmoid passes per element)')
+                             + ', DESIGN.md section 4') if tc_mode
                             else 'fp32 FFMA cross-check path: dense layers on the CUDA cores'}
         elif avg.get('edges'):
             # radius-graph / small-batch configs are dominated by K0 (neighbour list): integer + fp64 work whose
