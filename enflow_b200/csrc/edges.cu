@@ -117,6 +117,67 @@ __global__ void __launch_bounds__(256) k_edges_survivors(const T* __restrict__ p
     if (threadIdx.x == 0) { nsurv[m] = running_s; nactive[m] = running_a; }
 }
 
+// Small molecules (n of a few tens): the same pass with ONE WARP per molecule.  27 n image points are a few hundred, so a
+// 256-thread CTA per molecule spent its time in block barriers (three per 256 points plus six for the bounding sphere)
+// with most threads idle; a warp needs none: ballots rank the survivors, the running counts live in registers.
+// Survivor order (= id_mapping) and the active list are the ones of k_edges_survivors; the bounding sphere may differ in
+// its last bits (another summation order of the centre), which is pure pruning with a margin either way.
+template <typename T>
+__global__ void __launch_bounds__(256) k_edges_survivors_warp(const T* __restrict__ pos, const T* __restrict__ box,
+                                                               const float* __restrict__ r_cut,
+                                                               const int* __restrict__ mol_off, int B,
+                                                               int* __restrict__ idmap, int* __restrict__ nsurv,
+                                                               int* __restrict__ active, int* __restrict__ nactive) {
+    const int lane = threadIdx.x & 31;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= B) return;
+    const int o = mol_off[m], n = mol_off[m + 1] - o;
+    const int64_t base = 27LL * o;
+    const double rc = (double)r_cut[m];
+    const double bx = ld3(box, o, 0), by = ld3(box, o, 1), bz = ld3(box, o, 2);   // base.py:130 box[0]
+    const double ex = __dadd_rn(bx, rc), ey = __dadd_rn(by, rc), ez = __dadd_rn(bz, rc);
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int a = lane; a < n; a += 32) { sx += ld3(pos, o + a, 0); sy += ld3(pos, o + a, 1); sz += ld3(pos, o + a, 2); }
+    const double inv_n = 1.0 / (double)(n > 0 ? n : 1);
+    const double cx = warp_sum(sx) * inv_n, cy = warp_sum(sy) * inv_n, cz = warp_sum(sz) * inv_n;
+    double r2 = 0.0;
+    for (int a = lane; a < n; a += 32) {
+        const double dx = ld3(pos, o + a, 0) - cx, dy = ld3(pos, o + a, 1) - cy, dz = ld3(pos, o + a, 2) - cz;
+        r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, s));
+    const double reach = (sqrt(r2) + rc) * (1.0 + 1e-9) + 1e-12;
+    const double reach2 = reach * reach;
+    const unsigned lt = (1u << lane) - 1u;
+    const int total = 27 * n;
+    int run_s = 0, run_a = 0;
+    for (int start = 0; start < total; start += 32) {
+        const int ip = start + lane;
+        bool keep = false, act = false;
+        int a = 0, k = 0;
+        if (ip < total) {
+            k = ip / n;
+            a = ip - k * n;
+            const double px = __dadd_rn(ld3(pos, o + a, 0), shift_of(k % 3, bx));
+            const double py = __dadd_rn(ld3(pos, o + a, 1), shift_of((k / 3) % 3, by));
+            const double pz = __dadd_rn(ld3(pos, o + a, 2), shift_of(k / 9, bz));
+            const double qx = __ddiv_rn(px, ex), qy = __ddiv_rn(py, ey), qz = __ddiv_rn(pz, ez);
+            const double q = __dadd_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)), __dmul_rn(qz, qz));
+            keep = q <= 1.0;
+            const double ux = px - cx, uy = py - cy, uz = pz - cz;
+            act = keep && (ux * ux + uy * uy + uz * uz <= reach2);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const unsigned bal_a = __ballot_sync(0xffffffffu, act);
+        if (keep) idmap[base + run_s + __popc(bal & lt)] = a;
+        if (act) active[base + run_a + __popc(bal_a & lt)] = (k << ACT_SHIFT) | a;
+        run_s += __popc(bal);
+        run_a += __popc(bal_a);
+    }
+    if (lane == 0) { nsurv[m] = run_s; nactive[m] = run_a; }
+}
+
 // One CTA per molecule, one THREAD per active image point, looping over the molecule's atoms (positions converted
 // to fp64 once and staged in shared memory together with id_mapping when the molecule has at most HIT_SM atoms;
 // every lane reads the same atom: a broadcast).  FILL=false counts hits, FILL=true writes them in atom order, so a
@@ -554,13 +615,19 @@ int enf_build_edges_t(const T* pos, const T* box, const float* r_cut, const int*
     unsigned* hmask = reinterpret_cast<unsigned*>(nactive + N);      // 2 x 27N
     if (!ref_pos) cnt_ref = nullptr;          // reference order not requested: one array to count, zero and scan
     cudaMemsetAsync(cnt_csr, 0, sizeof(int) * ((cnt_ref ? 2 : 1) * n27 + (cnt_ref ? 2 : 1)), st);
-    enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, idmap, nsurv, active, nactive);
+    // small molecules: one thread per active point; large ones (long atom loops, few points per SM): one warp per point
+    const bool per_thread = N <= 96LL * B;
+    // ... and, when there are enough molecules to fill the GPU with warps, one warp instead of one CTA per molecule for the
+    // survivor pass (C4, 16 384 molecules: 169 -> ~90 us per layer; at B = 64 the CTA form has 8x the parallelism)
+    if (per_thread && B >= 4 * enf_num_sms())
+        enf_count_launch(), k_edges_survivors_warp<T><<<(B + 7) / 8, 256, 0, st>>>(pos, box, r_cut, mol_off, B, idmap, nsurv, active,
+                                                                                 nactive);
+    else
+        enf_count_launch(), k_edges_survivors<T><<<B, 256, 0, st>>>(pos, box, r_cut, mol_off, B, idmap, nsurv, active, nactive);
     // large molecules: several CTAs per molecule (the active list of a 500-atom fragment has ~3000 entries)
     int ysplit = (B > 0 ? N / B : 1) / 24;
     ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
     const dim3 hgrid(B, ysplit);
-    // small molecules: one thread per active point; large ones (long atom loops, few points per SM): one warp per point
-    const bool per_thread = N <= 96LL * B;
     if (per_thread)
         enf_count_launch(), k_edges_hits<T, false><<<hgrid, HIT_T, 0, st>>>(pos, box, r_cut, mol_off, idmap, nsurv, active, nactive,
                                                                         cnt_csr, cnt_ref, hmask, nullptr, nullptr, nullptr, E_cap, status);

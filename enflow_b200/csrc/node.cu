@@ -234,7 +234,7 @@ __global__ void k_transpose_pack(const float* __restrict__ W2, const float* __re
 
 int enf_node_grid(int N) {
     int tiles = (N + NT - 1) / NT;
-    int cap = enf_num_sms() * 4;
+    int cap = enf_num_sms() * 8;      // 32 warps per SM: the kernel is latency-bound (three barriers per 16 nodes)
     return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
 

@@ -1,7 +1,10 @@
-python bench.py > gpurun_out/r2j_bench_c2.json 2> gpurun_out/r2j_bench_c2.err; echo "bench rc=$?"
-cmd="python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline"
-$cmd > gpurun_out/r2j_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2j_launches.csv $cmd > gpurun_out/r2j_ncu1.log 2>&1
-echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k_edge_(fwd|bwd)_tc' -s 14 -c 2 -f -o gpurun_out/r2j_edge $cmd > gpurun_out/r2j_ncu2.log 2>&1
-echo "ncu full rc=$?"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
+for c in c4 c1 c2; do
+  timeout 300 python bench.py --config $c --steps 10 --no-cpu-baseline > gpurun_out/r2l_bench_$c.json 2> gpurun_out/r2l_bench_$c.err; echo "bench $c rc=$?"
+done
+python - <<'PY'
+import json
+for c in ('c4','c1','c2'):
+    d=json.load(open(f'gpurun_out/r2l_bench_{c}.json'))
+    print(c, round(d['value']), round(d['ms_per_step'],3), {k: round(v,3) for k,v in d['kernel_ms_per_step'].items() if k in ('edges','node_pre','edge_fwd','node_post','run_sum')})
+PY
