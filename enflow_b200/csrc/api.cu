@@ -41,6 +41,41 @@ void enf_time_end(cudaStream_t st) {
     cudaEventRecord(g_slots[g_used].b, st);
     ++g_used;
 }
+bool enf_timing_on() { return g_timing; }
+
+// ---- side streams and the events that order them against the caller's stream
+static cudaStream_t g_side[2] = {nullptr, nullptr};
+static cudaEvent_t g_chain_ev[64];
+static cudaEvent_t g_mark_ev[8];
+static int g_chain_next = 0;
+static bool g_side_made = false;
+static void side_make() {
+    if (g_side_made) return;
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 64; ++i) cudaEventCreateWithFlags(&g_chain_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&g_mark_ev[i], cudaEventDisableTiming);
+    g_side_made = true;
+}
+cudaStream_t enf_side_stream(int which) {
+    side_make();
+    return g_side[which & 1];
+}
+void enf_mark(int id, cudaStream_t st) {
+    side_make();
+    cudaEventRecord(g_mark_ev[id & 7], st);
+}
+void enf_wait_mark(int id, cudaStream_t st) {
+    side_make();
+    cudaStreamWaitEvent(st, g_mark_ev[id & 7], 0);
+}
+void enf_chain(cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
+    side_make();
+    cudaEvent_t ev = g_chain_ev[g_chain_next];       // a wait refers to the record made just before it: reuse is safe
+    g_chain_next = (g_chain_next + 1) & 63;
+    cudaEventRecord(ev, from);
+    cudaStreamWaitEvent(to, ev, 0);
+}
 
 #pragma GCC visibility push(default)
 extern "C" {

@@ -21,6 +21,15 @@ enum { TK_EDGES = 0, TK_NODE_PRE, TK_EDGE_FWD, TK_RUN_SUM, TK_SEG_COLS, TK_SEG_R
        TK_COUPLING_BWD, TK_COUPLING_INV, TK_EDGE_GEOM, TK_EDGE_BWD, TK_EDGE_REDUCE, TK_NODE_POST_BWD, TK_NODE_PRE_BWD,
        TK_COL_PERM, TK_ARGMAX, TK_NLL, TK_COUNT };
 void enf_time_begin(int kind, cudaStream_t st);
+bool enf_timing_on();
+// `to` waits for everything enqueued on `from` so far (event record + stream wait; capturable); no-op when from == to
+void enf_chain(cudaStream_t from, cudaStream_t to);
+// library-owned side streams (created once per process = once per device); [0] carries the weight-gradient reductions,
+// kernels that nothing on the main stream waits for until the end of the backward pass
+cudaStream_t enf_side_stream(int which);
+// named events (id 0..7) for dependencies that are not "everything so far": record on one stream, wait on another
+void enf_mark(int id, cudaStream_t st);
+void enf_wait_mark(int id, cudaStream_t st);
 void enf_time_end(cudaStream_t st);
 
 #define ENF_CHECK_ARG(cond, ...)                 \

@@ -659,11 +659,26 @@ int64_t enf_edge_bwd_geom_bytes(int E_cap) {
     return tiles * IDX_BYTES + tiles * TE * (4 + 4 + 12 + 12) + tiles * 4 * (int64_t)sizeof(int2) + 256;
 }
 
-int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
-                    const float* pos, const float* box, const float* P, const float* S, const float* lp,
-                    const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
-                    float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
-                    float* partial, unsigned char* geom, int* status, cudaStream_t st) {
+// the per-tile edge records of the backward kernel (needs dF of this layer's coupling step; nothing else of the layer)
+int enf_edge_bwd_tc_geom(const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap, const float* pos,
+                         const float* box, const float* s_saved, const float* dF, float coords_weight, const int* mis,
+                         unsigned char* geom, cudaStream_t st) {
+    if (E_cap == 0) return ENF_OK;
+    const int slots = (E_cap + TE - 1) / TE * TE;
+    int ggrid = (slots + 255) / 256;
+    if (ggrid > 8 * enf_num_sms()) ggrid = 8 * enf_num_sms();
+    enf_time_begin(TK_EDGE_GEOM, st);
+    enf_count_launch(), k_edge_geom_bwd<<<ggrid, 256, 0, st>>>(row, col, rowptr, E_dev, pos, box, s_saved, dF, coords_weight, mis, geom, E_cap);
+    enf_time_end(st);
+    ENF_CHECK_LAUNCH();
+    return ENF_OK;
+}
+
+// the backward kernel on `st` (the records must be complete on `st`), the reduction of its per-CTA weight-gradient
+// partials on `st_red` (== st: in line)
+int enf_edge_bwd_tc(int mode, const int* E_dev, int E_cap, const float* P, const float* S, const float* lp,
+                    const unsigned char* wimg, int nf, const float* dagg, float* runs, float* dz1, float* dd, float* lgrad,
+                    float* partial, unsigned char* geom, int* status, cudaStream_t st, cudaStream_t st_red) {
     if (E_cap == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const int grid = enf_num_sms();
@@ -673,12 +688,6 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
         cudaFuncSetAttribute(k_edge_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemB<false>::total);
         attr = true;
     }
-    const int slots = (E_cap + TE - 1) / TE * TE;
-    int ggrid = (slots + 255) / 256;
-    if (ggrid > 8 * enf_num_sms()) ggrid = 8 * enf_num_sms();
-    enf_time_begin(TK_EDGE_GEOM, st);
-    enf_count_launch(), k_edge_geom_bwd<<<ggrid, 256, 0, st>>>(row, col, rowptr, E_dev, pos, box, s_saved, dF, coords_weight, mis, geom, E_cap);
-    enf_time_end(st);
     const GeomView gv = geom_view(geom, E_cap);
     enf_time_begin(TK_EDGE_BWD, st);
     if (mode == 1)
@@ -691,8 +700,9 @@ int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr,
             runs, dz1, dd, partial, status);
     enf_time_end(st);
     ENF_CHECK_LAUNCH();
-    enf_time_begin(TK_EDGE_REDUCE, st);
-    const int rc = enf_edge_reduce_partials(partial, grid, lgrad, nf, st);
-    enf_time_end(st);
+    enf_chain(st, st_red);
+    enf_time_begin(TK_EDGE_REDUCE, st_red);
+    const int rc = enf_edge_reduce_partials(partial, grid, lgrad, nf, st_red);
+    enf_time_end(st_red);
     return rc;
 }

@@ -2,6 +2,7 @@
 // (enflow/flow/dynamics.py:10-37) as one stream-ordered sequence of kernel launches per call.
 // No allocation and no host synchronisation happen here: the caller provides one workspace that is
 // carved deterministically from the dims, and data-dependent sizes (edge counts) stay on the device.
+#include <stdlib.h>
 #include "internal.h"
 
 struct enflow_dims_t {
@@ -19,6 +20,9 @@ struct enflow_dims_t {
     } while (0)
 
 namespace {
+
+// side streams are used whenever the per-family timing (eager, one event pair per kernel family on the caller's stream) is off
+bool side_ok() { return !enf_timing_on(); }
 
 struct Bump {
     char* base;
@@ -53,7 +57,8 @@ struct Workspace {
     double* logq_mol;
     float* log_q;
     // backward scratch
-    float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd, *partial;
+    float *dQ, *dF, *dG, *dagg, *dP, *dS, *dz1, *dd;
+    float *partial, *partial_post, *partial_pre;      // per-CTA weight-gradient partials: edge kernel (and argmax), node_post, node_pre
     unsigned char* geom;     // per-tile edge records of the tensor-core backward kernel
     int *colptr, *perm, *same;
     size_t bytes;
@@ -109,6 +114,8 @@ Workspace carve(const enflow_dims_t& d, void* base, int training) {
         w.dagg = b.take<float>(N * H); w.dP = b.take<float>(N * H); w.dS = b.take<float>(N * H);
         w.dz1 = b.take<float>(E * H); w.dd = b.take<float>(E * 3);
         w.partial = b.take<float>(partial_floats(d));
+        w.partial_post = b.take<float>((size_t)enf_node_post_partial_floats(d.N, d.nf));
+        w.partial_pre = b.take<float>((size_t)enf_node_pre_partial_floats(d.N, d.nf));
         w.geom = d.mode ? b.take<unsigned char>((size_t)enf_edge_bwd_geom_bytes(d.E_cap)) : nullptr;
         w.colptr = b.take<int>(N + 1); w.perm = b.take<int>(E); w.same = b.take<int>(4);
     }
@@ -254,6 +261,13 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
     ENF_CHECK_ARG(workspace_bytes >= w.bytes, "workspace too small: %zu < %zu", workspace_bytes, w.bytes);
     const int nf = d.nf;
     if (d.B == 0 || d.N == 0) return ENF_OK;
+    // Tensor-core modes: the reductions of the per-CTA weight-gradient partials (three per layer, nothing reads their result
+    // before the optimizer) run on a side stream, in order, beside the kernels of the main chain (C2: 6.04 -> 5.96 ms per
+    // step).  Each producer has its own partial buffer and waits for the reduction that last read it (one layer earlier:
+    // long finished).  (Also tried: the per-tile edge records and the regime check on a second side stream: no gain.)
+    const bool par = d.mode != 0 && side_ok();
+    cudaStream_t red = par ? enf_side_stream(0) : st;
+    enf_chain(st, red);                               // the gradient buffer is ready on st (zeroed by the caller)
     for (int l = d.L - 1; l >= 0; --l) {
         const LayerSave& sv = w.layer[l];
         const float* lp = layer_params(params, nf, l);
@@ -264,9 +278,12 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
         if (d.mode == 0)
             TIMED(TK_NODE_POST_BWD, enf_node_post_bwd(w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp,
                                                  w.packed + (int64_t)l * enf_pack_offsets(nf).size, w.dagg, dh, lg, w.partial, st));
-        else
+        else {
+            if (par && l < d.L - 1) enf_wait_mark(0, st);      // (layer l + 1's reduction has read partial_post: long ago)
             TIMED(TK_NODE_POST_BWD, enf_node_post_bwd_tc(d.mode, w.h[l], sv.agg, sv.z4, w.dG, d.N, nf, lp, tc_image(w, l), w.dagg,
-                                                    dh, lg, w.partial, st));
+                                                    dh, lg, w.partial_post, st, red));
+            if (par) enf_mark(0, red);
+        }
         // edge_model + force_model (egcl.py:57-63,71-75); P/S were kept by the forward pass
         // column-grouped view of the edges; reused as is when this layer's list equals the one just processed
         // (fully connected regime: the neighbour list is the same at every coupling step)
@@ -286,17 +303,24 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
                                             w.partial, st));
             TIMED(TK_SEG_ROWS, enf_segment_sum128(w.dz1, sv.rowptr, nullptr, d.N, d.E_cap, 0, w.dP, st));
         } else {
-            ENF_TRY(enf_edge_bwd_tc(d.mode, sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.P,
-                                               sv.S, lp, tc_image(w, l), nf, sv.s, w.dagg, w.dF, d.coords_weight, sv.mis,
-                                               w.runs, w.dz1, w.dd, lg, w.partial, w.geom, status, st));      // (times its three kernels itself)
+            ENF_TRY(enf_edge_bwd_tc_geom(sv.row, sv.col, sv.rowptr, sv.E_dev, d.E_cap, w.pos[l], box, sv.s, w.dF, d.coords_weight,
+                                         sv.mis, w.geom, st));
+            if (par && l < d.L - 1) enf_wait_mark(1, st);
+            ENF_TRY(enf_edge_bwd_tc(d.mode, sv.E_dev, d.E_cap, sv.P, sv.S, lp, tc_image(w, l), nf, w.dagg, w.runs, w.dz1, w.dd, lg,
+                                    w.partial, w.geom, status, st, red));      // (times its kernels itself)
+            if (par) enf_mark(1, red);
             // dP and the row half of dpos (coord_diff = pos[row] - pos[col], data/base.py:17: +dd onto row atoms)
             TIMED(TK_RUN_SUM, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
         }
         if (d.mode == 0) TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
         // dS and the column half of dpos (-dd onto col atoms), both through the column permutation
         TIMED(TK_SEG_COLS, enf_segment_sum128_sum3(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, w.dd, -1.0f, dpos, st));
-        TIMED(TK_NODE_PRE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, w.partial, st));
+        if (par && l < d.L - 1) enf_wait_mark(2, st);
+        TIMED(TK_NODE_PRE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, d.mode != 0 ? w.partial_pre : w.partial, st,
+                                                 d.mode != 0 ? red : st));
+        if (par) enf_mark(2, red);
     }
+    enf_chain(red, st);                               // every weight gradient is in place before the caller goes on
     if (eps)
         TIMED(TK_ARGMAX, enf_argmax_bwd(h_in, eps, d.N, nf, argmax_params(params, nf, d.L), dh, dldj,
                                argmax_params(grads, nf, d.L), w.partial, st));

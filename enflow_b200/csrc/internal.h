@@ -27,7 +27,7 @@ int enf_pack_layer(const float* layer_params, int nf, float* packed, cudaStream_
 int enf_node_pre_fwd(const float* h, int N, int nf, const float* lp, float* P, float* S, float* Q, cudaStream_t st);
 int64_t enf_node_pre_partial_floats(int N, int nf);
 int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float* dP, const float* dS,
-                     const float* dQ, float* dh, float* lgrad, float* partial, cudaStream_t st);
+                     const float* dQ, float* dh, float* lgrad, float* partial, cudaStream_t st, cudaStream_t st_red);
 int enf_node_post_fwd(const float* h, const float* agg, int N, int nf, const float* lp, const float* packed,
                       float* z4, float* G, cudaStream_t st);
 int64_t enf_node_post_partial_floats(int N, int nf);
@@ -90,18 +90,19 @@ int enf_edge_fwd_tc(int mode, const int* row, const int* col, const int* E_dev, 
                     const float* box, const float* P, const float* S, const float* lp, const unsigned char* wimg,
                     int nf, const int* rowptr, const int* mis, float* runs, float* s_out, float* trans,
                     cudaStream_t st);
-int enf_edge_bwd_tc(int mode, const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap,
-                    const float* pos, const float* box, const float* P, const float* S, const float* lp,
-                    const unsigned char* wimg, int nf, const float* s_saved, const float* dagg, const float* dF,
-                    float coords_weight, const int* mis, float* runs, float* dz1, float* dd, float* lgrad,
-                    float* partial, unsigned char* geom, int* status, cudaStream_t st);
+int enf_edge_bwd_tc_geom(const int* row, const int* col, const int* rowptr, const int* E_dev, int E_cap, const float* pos,
+                         const float* box, const float* s_saved, const float* dF, float coords_weight, const int* mis,
+                         unsigned char* geom, cudaStream_t st);
+int enf_edge_bwd_tc(int mode, const int* E_dev, int E_cap, const float* P, const float* S, const float* lp,
+                    const unsigned char* wimg, int nf, const float* dagg, float* runs, float* dz1, float* dd, float* lgrad,
+                    float* partial, unsigned char* geom, int* status, cudaStream_t st, cudaStream_t st_red);
 int64_t enf_edge_bwd_geom_bytes(int E_cap);
 // tensor-core node_model (node_tc.cu); weight images live behind the edge images in the same per-layer buffer
 int enf_node_post_fwd_tc(int mode, const float* h, const float* agg, int N, int nf, const float* lp,
                          const unsigned char* wimg, float* z4, float* G, cudaStream_t st);
 int enf_node_post_bwd_tc(int mode, const float* h, const float* agg, const float* z4, const float* dG, int N, int nf,
                          const float* lp, const unsigned char* wimg, float* dagg, float* dh, float* lgrad,
-                         float* partial, cudaStream_t st);
+                         float* partial, cudaStream_t st, cudaStream_t st_red);
 // per-run partial segment sums (segment.cu): mis = N+2 ints, runs = enf_run_rows(E_cap, N) x 128 floats
 int64_t enf_scan_scratch_ints(int64_t n);
 int enf_run_index(const int* rowptr, int N, int* mis, int* scratch, cudaStream_t st);

@@ -268,7 +268,7 @@ int64_t enf_node_pre_partial_floats(int N, int nf) {
 }
 
 int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float* dP, const float* dS,
-                     const float* dQ, float* dh, float* lgrad, float* partial, cudaStream_t st) {
+                     const float* dQ, float* dh, float* lgrad, float* partial, cudaStream_t st, cudaStream_t st_red) {
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
     const int grid = node_pre_bwd_grid(N);
@@ -288,7 +288,8 @@ int enf_node_pre_bwd(const float* h, int N, int nf, const float* lp, const float
     const int dsts[6] = {(int)o.off[P_W1], (int)o.off[P_B1], (int)o.off[P_W6], (int)o.off[P_B6], (int)o.off[P_W7],
                          (int)o.off[P_B7]};
     for (int i = 0; i < 6; ++i) { s.src[i] = src; s.dst[i] = dsts[i]; s.len[i] = lens[i]; src += lens[i]; }
-    enf_count_launch(), k_reduce_partials<<<(src + 31) / 32, 256, 0, st>>>(partial, grid, src, s, lgrad);
+    enf_chain(st, st_red);
+    enf_count_launch(), k_reduce_partials<<<(src + 31) / 32, 256, 0, st_red>>>(partial, grid, src, s, lgrad);
     ENF_CHECK_LAUNCH();
     return ENF_OK;
 }

@@ -489,7 +489,7 @@ int enf_node_post_fwd_tc(int mode, const float* h, const float* agg, int N, int 
 
 int enf_node_post_bwd_tc(int mode, const float* h, const float* agg, const float* z4, const float* dG, int N, int nf,
                          const float* lp, const unsigned char* wimg, float* dagg, float* dh, float* lgrad,
-                         float* partial, cudaStream_t st) {
+                         float* partial, cudaStream_t st, cudaStream_t st_red) {
     (void)mode;
     if (N == 0) return ENF_OK;
     const EgclOffsets o = enf_egcl_offsets(nf);
@@ -502,5 +502,6 @@ int enf_node_post_bwd_tc(int mode, const float* h, const float* agg, const float
     enf_count_launch(), k_node_post_bwd_tc<true><<<grid, THREADS, SmemB<true>::total, st>>>(
         h, agg, z4, dG, N, nf, lp + o.off[P_W5], wimg, dagg, dh, partial);
     ENF_CHECK_LAUNCH();
-    return enf_node_post_reduce(partial, grid, nf, lgrad, st);
+    enf_chain(st, st_red);                  // the partial reduction runs beside whatever follows on st
+    return enf_node_post_reduce(partial, grid, nf, lgrad, st_red);
 }
