@@ -309,12 +309,16 @@ extern "C" int enflow_flow_backward(const enflow_dims_t* dims, const float* para
             ENF_TRY(enf_edge_bwd_tc(d.mode, sv.E_dev, d.E_cap, sv.P, sv.S, lp, tc_image(w, l), nf, w.dagg, w.runs, w.dz1, w.dd, lg,
                                     w.partial, w.geom, status, st, red));      // (times its kernels itself)
             if (par) enf_mark(1, red);
-            // dP and the row half of dpos (coord_diff = pos[row] - pos[col], data/base.py:17: +dd onto row atoms)
-            TIMED(TK_RUN_SUM, enf_run_sum128_sum3(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, w.dd, 0, 1.0f, 1, dpos, st));
+            // dP = the rows' run sums: on the side stream (behind this layer's edge reduction), beside the column sum below
+            TIMED(TK_RUN_SUM, enf_run_sum128(w.runs, sv.rowptr, sv.mis, d.N, d.E_cap, w.dP, red));
+            if (par) enf_mark(3, red);
         }
         if (d.mode == 0) TIMED(TK_SEG3, enf_segment_sum3(w.dd, sv.rowptr, nullptr, d.N, d.E_cap, 0, 1.0f, 1, dpos, st));
-        // dS and the column half of dpos (-dd onto col atoms), both through the column permutation
-        TIMED(TK_SEG_COLS, enf_segment_sum128_sum3(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, w.dd, -1.0f, dpos, st));
+        // dS through the column permutation, and d loss / d pos: +dd onto row atoms (coord_diff = pos[row] - pos[col],
+        // data/base.py:17), then -dd onto col atoms through the permutation (tensor-core modes: both in this launch)
+        TIMED(TK_SEG_COLS, enf_segment_sum128_sum3(w.dz1, w.colptr, w.perm, d.N, d.E_cap, 0, w.dS, w.dd, -1.0f, dpos,
+                                                   d.mode != 0 ? sv.rowptr : nullptr, st));
+        if (par) enf_wait_mark(3, st);                       // dP is complete
         if (par && l < d.L - 1) enf_wait_mark(2, st);
         TIMED(TK_NODE_PRE_BWD, enf_node_pre_bwd(w.h[l], d.N, nf, lp, w.dP, w.dS, w.dQ, dh, lg, d.mode != 0 ? w.partial_pre : w.partial, st,
                                                  d.mode != 0 ? red : st));

@@ -110,7 +110,7 @@ int enf_run_sum128(const float* runs, const int* rowptr, const int* mis, int N, 
 int enf_run_sum128_sum3(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out,
                         const float* x3, int mean3, float scale3, int accumulate3, float* out3, cudaStream_t st);
 int enf_segment_sum128_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
-                            const float* x3, float scale3, float* out3, cudaStream_t st);
+                            const float* x3, float scale3, float* out3, const int* rowptr3, cudaStream_t st);
 inline int64_t enf_run_rows(int E_cap, int N) { return (int64_t)E_cap / 16 + N + 2; }
 int enf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int* step, float lr, const float* lr_dev,
                   float beta1, float beta2, float eps, cudaStream_t st);

@@ -37,7 +37,8 @@ template <bool SILU, bool PERM>
 __global__ void __launch_bounds__(256) k_segment_sum128(const float* __restrict__ x, const int* __restrict__ ptr,
                                                          const int* __restrict__ perm, int N, int E_cap,
                                                          float* __restrict__ out, const float* __restrict__ x3,
-                                                         float scale3, float* __restrict__ out3) {
+                                                         float scale3, float* __restrict__ out3,
+                                                         const int* __restrict__ rowptr3) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int ii = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ii < N; ii += warps_per_grid) {
@@ -69,7 +70,18 @@ __global__ void __launch_bounds__(256) k_segment_sum128(const float* __restrict_
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         reinterpret_cast<float4*>(out + (int64_t)i * ENF_H)[lane] = acc;
-        if (x3) row_sum3<PERM>(x3, perm, e0, e1, i, lane, 0, scale3, 1, out3);      // out3 += scale3 * sum
+        if (x3) {
+            // rowptr3: first out3 += the DIRECT sum of x3 over row i's own edges, then the (permuted) segment's share:
+            // both halves of d loss / d pos (data/base.py:17) in one launch, in the order two launches used to add them
+            if (rowptr3) {
+                const int r0 = rowptr3[i];
+                int r1 = rowptr3[i + 1];
+                if (r1 > E_cap) r1 = E_cap;
+                row_sum3<false>(x3, nullptr, r0, r1, i, lane, 0, 1.0f, 1, out3);
+                __syncwarp();
+            }
+            row_sum3<PERM>(x3, perm, e0, e1, i, lane, 0, scale3, 1, out3);      // out3 += scale3 * sum
+        }
     }
 }
 
@@ -153,7 +165,7 @@ int enf_run_index(const int* rowptr, int N, int* mis, int* scratch, cudaStream_t
 int enf_run_sum128_sum3(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out,
                         const float* x3, int mean3, float scale3, int accumulate3, float* out3, cudaStream_t st);
 int enf_segment_sum128_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
-                            const float* x3, float scale3, float* out3, cudaStream_t st);
+                            const float* x3, float scale3, float* out3, const int* rowptr3, cudaStream_t st);
 
 int enf_run_sum128(const float* runs, const int* rowptr, const int* mis, int N, int E_cap, float* out, cudaStream_t st) {
     return enf_run_sum128_sum3(runs, rowptr, mis, N, E_cap, out, nullptr, 0, 0.f, 0, nullptr, st);
@@ -171,20 +183,21 @@ int enf_run_sum128_sum3(const float* runs, const int* rowptr, const int* mis, in
 
 int enf_segment_sum128(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
                        cudaStream_t st) {
-    return enf_segment_sum128_sum3(x, ptr, perm, N, E_cap, apply_silu, out, nullptr, 0.f, nullptr, st);
+    return enf_segment_sum128_sum3(x, ptr, perm, N, E_cap, apply_silu, out, nullptr, 0.f, nullptr, nullptr, st);
 }
 
-// the 128-wide segment sum and (x3 != NULL) out3 += scale3 * the 3-vector segment sum over the same segments
+// the 128-wide segment sum and (x3 != NULL) out3 += scale3 * the 3-vector segment sum over the same segments;
+// rowptr3 != NULL: before that, out3 += the direct sum of x3 over the CSR row of the same index
 int enf_segment_sum128_sum3(const float* x, const int* ptr, const int* perm, int N, int E_cap, int apply_silu, float* out,
-                            const float* x3, float scale3, float* out3, cudaStream_t st) {
+                            const float* x3, float scale3, float* out3, const int* rowptr3, cudaStream_t st) {
     if (N == 0) return ENF_OK;
     const int blocks = min((N + 7) / 8, enf_num_sms() * 8);
     if (perm) {
-        if (apply_silu) enf_count_launch(), k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
-        else enf_count_launch(), k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
+        if (apply_silu) enf_count_launch(), k_segment_sum128<true, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3, rowptr3);
+        else enf_count_launch(), k_segment_sum128<false, true><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3, rowptr3);
     } else {
-        if (apply_silu) enf_count_launch(), k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
-        else enf_count_launch(), k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3);
+        if (apply_silu) enf_count_launch(), k_segment_sum128<true, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3, rowptr3);
+        else enf_count_launch(), k_segment_sum128<false, false><<<blocks, 256, 0, st>>>(x, ptr, perm, N, E_cap, out, x3, scale3, out3, rowptr3);
     }
     ENF_CHECK_LAUNCH();
     return ENF_OK;

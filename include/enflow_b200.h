@@ -8,7 +8,11 @@
  *   - every pointer is a DEVICE pointer unless it says "host"; floats are fp32, indices int32;
  *   - the caller owns all memory (inputs, outputs, workspace); the library never allocates or frees
  *     device memory and keeps no reference after a call returns (calls are stream-ordered);
- *   - `stream` is a cudaStream_t passed as void*;
+ *   - `stream` is a cudaStream_t passed as void*; all work of a call is ordered after what was enqueued on it before
+ *     the call and before what is enqueued after it.  enflow_flow_backward additionally runs its weight-gradient
+ *     reductions on one library-owned non-blocking stream (created on first use, on the device current then: one
+ *     process per GPU, one host thread per process, as in the reference), forked from and joined back into `stream`
+ *     inside the call with events, so the call is capturable in a CUDA graph like any other;
  *   - return value 0 = ok; non-zero = failure, message from enflow_last_error() (thread-local);
  *   - `status` (int[1], device) receives OR-ed flags: 1 = edge capacity exceeded (E > E_cap),
  *     2 = the reference's id_mapping lookup would have raised IndexError (data/base.py:137),
