@@ -480,6 +480,20 @@ def main():
                     'peak_source': pk['source'] + ' HBM copy bandwidth', 'algorithmic_bytes_per_launch': k0_bytes,
                     'note': f'dominant family of this config is {dom}; K0 is latency-bound fp64 image tests over 27 n points per '
                             'molecule, far from the HBM roofline by construction (DESIGN.md section 4)'}
+        # the other tensor-core edge kernel (same arithmetic as `roofline`, its own timing family)
+        tensor_other = {}
+        if tc_mode and roof is not None and roof.get('bound') == 'tensor':
+            for other in ('edge_fwd', 'edge_bwd'):
+                if other != dom and avg.get(other):
+                    a = flops[other] / (avg[other] * 1e-3) / 1e12
+                    kn = 'k_' + other + '_tc'
+                    n2 = ncu_summary(kn + ('<1>' if args.precision == 'fp32_tc' else '<0>')) \
+                        if (args.config == 'c2' and batch == 1024) else None
+                    tensor_other[other] = {'kernel': kn, 'bound': 'tensor', 'achieved': a, 'peak': pk['bf16_sustained'],
+                                           'unit': 'TFLOP/s', 'frac': a / pk['bf16_sustained'], 'avg_launch_ms': avg[other],
+                                           'algorithmic_flops_per_launch': flops[other],
+                                           'traffic': n2['traffic'] if n2 else None,
+                                           'pipe_tensor_active_pct': n2['pipe_tensor_active_pct'] if n2 else None}
         # the HBM-bound kernels the north star names (SURVEY 8d byte counts), each from its OWN timing family
         hbm = {}
         seg_bytes = E * H * 4 + (n_atoms + 1) * 4 + n_atoms * H * 4
@@ -504,12 +518,15 @@ def main():
             'launch_mode': graph_note,
             'eager_ms_per_step': ms_eager / args.steps,
             'roofline': roof,
+            'roofline_tensor_kernels': tensor_other,
             'roofline_hbm_kernels': hbm,
             'kernel_ms_per_step': {k: v[0] / args.steps for k, v in fam.items()},
             'kernel_share_of_step': share,
             'kernel_timing_note': 'kernel_ms_per_step / kernel_share_of_step come from the eagerly launched pass '
-                                  '(eager_ms_per_step, CUDA events around every kernel family); ms_per_step is the graph replay, '
-                                  'so the family times sum to more than ms_per_step',
+                                  '(eager_ms_per_step, CUDA events around every kernel family, everything on one stream); ms_per_step '
+                                  'is the graph replay, in which the weight-gradient reductions and the row run sums of the '
+                                  'backward pass run on a side stream beside the main chain, so the family times sum to more '
+                                  'than ms_per_step',
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = {'c1': 64, 'c2': 48, 'c3': 12, 'c4': 256, 'c5': 1}[args.config]
