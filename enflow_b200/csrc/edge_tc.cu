@@ -1,6 +1,5 @@
 // Weight images of the tensor-core kernels: fp32 parameters -> swizzled bf16 operand images (hi and lo of the bf16x3
 // split), all layers in two launches; and the entry point of the forward edge kernel (edge_tc_fwd.cu).
-#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 

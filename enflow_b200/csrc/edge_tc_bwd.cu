@@ -28,7 +28,7 @@
 //     windows of A and B disjoint except for one GEMM (G4(b) in front of E2(a')), which is the one exposed wait per
 //     two tiles.  bf16 mode has room for a dz buffer per pipeline (no exposed wait).
 //   * silu'(z2) of a tile (needed two tasks later) is parked in 64 spare TMEM columns per pipeline instead of
-//     registers (tcgen05.st / tcgen05.ld), which is what lets two tiles' state fit in 120 registers per thread.
+//     registers (tcgen05.st / tcgen05.ld), which is what lets two tiles' state fit in the ~100 registers per thread that 20 warps leave.
 //
 // Thread map of the epilogue warps: warp w owns TMEM lanes [32 (w%4), +32) = hidden units n and tile edges
 // [16 (w/4), +16).  Per-tile edge data (k_edge_geom_bwd): row/col indices arrive in a 3-slot shared-memory ring by

@@ -2,7 +2,6 @@
 // (enflow/flow/dynamics.py:10-37) as one stream-ordered sequence of kernel launches per call.
 // No allocation and no host synchronisation happen here: the caller provides one workspace that is
 // carved deterministically from the dims, and data-dependent sizes (edge counts) stay on the device.
-#include <stdlib.h>
 #include "internal.h"
 
 struct enflow_dims_t {
