@@ -149,7 +149,7 @@ void copy_f(float* dst, const float* src, size_t n, cudaStream_t st) {
 // Q, F, G of one EGCL at the given node state (egcl.py:77-93); saves activations into `sv`
 int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv, const float* lp, const float* packed,
                  const unsigned char* tcimg, const float* h, const float* pos, const float* box, const float* r_cut, const int* mol_off,
-                 int* status, cudaStream_t st) {
+                 int* status, bool keep, cudaStream_t st) {
     if (d.fc)      // the list exists (fc_lists); prove that these positions are still in the regime where it is the answer
         TIMED(TK_EDGES, enf_fc_check(pos, box, r_cut, mol_off, d.B, status, st));
     else
@@ -174,7 +174,7 @@ int egcl_forward(const enflow_dims_t& d, const Workspace& w, const LayerSave& sv
     if (d.mode == 0)
         TIMED(TK_NODE_POST, enf_node_post_fwd(h, sv.agg, d.N, d.nf, lp, packed, sv.z4, w.G, st));
     else
-        TIMED(TK_NODE_POST, enf_node_post_fwd_tc(d.mode, h, sv.agg, d.N, d.nf, lp, tcimg, sv.z4, w.G, st));
+        TIMED(TK_NODE_POST, enf_node_post_fwd_tc(d.mode, h, sv.agg, d.N, d.nf, lp, tcimg, keep ? sv.z4 : nullptr, w.G, st));      // z4: backward only
     return ENF_OK;
 }
 
@@ -241,7 +241,7 @@ extern "C" int enflow_flow_forward(const enflow_dims_t* dims, const float* param
         float* vo = last ? vel_out : w.vel[nxt];
         const LayerSave& sv = w.layer[training ? l : 0];
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
-                             tc_image(w, l), w.h[cur], w.pos[cur], box, r_cut, mol_off, status, st));
+                             tc_image(w, l), w.h[cur], w.pos[cur], box, r_cut, mol_off, status, training != 0, st));
         TIMED(TK_COUPLING_FWD, enf_coupling_fwd(sv.Q, w.F, w.G, w.h[cur], w.g[cur], w.pos[cur], w.vel[cur], box, mol_off, d.B, nf, d.dt,
                                  ho, go, po, vo, ldj_mol, st));
     }
@@ -355,7 +355,7 @@ extern "C" int enflow_flow_reverse(const enflow_dims_t* dims, const float* param
     for (int l = d.L - 1; l >= 0; --l) {
         TIMED(TK_COUPLING_INV, enf_coupling_inv_pre(g, vel, box, d.N, nf, d.dt, h, pos, st));                    // dynamics.py:27-29
         ENF_TRY(egcl_forward(d, w, sv, layer_params(params, nf, l), w.packed + (int64_t)l * enf_pack_offsets(nf).size,
-                             tc_image(w, l), h, pos, box, r_cut, mol_off, status, st));                           // :31
+                             tc_image(w, l), h, pos, box, r_cut, mol_off, status, false, st));                    // :31
         TIMED(TK_COUPLING_INV, enf_coupling_inv_post(sv.Q, w.F, w.G, mol_off, d.B, nf, d.dt, g, vel, neg_ldj_mol, st));   // :32-33
     }
     if (quantize) ENF_TRY(enf_argmax_reverse(h, d.N, nf, st));                                    // :35

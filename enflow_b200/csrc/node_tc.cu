@@ -210,7 +210,7 @@ k_node_post_fwd_tc(const float* __restrict__ h, const float* __restrict__ agg, i
                 for (int j = 0; j < 8; ++j) {
                     const int node = t0 + 32 * cg + 8 * ch + j;
                     const float z = v[8 * ch + j] + b4n;
-                    if (node < N) z4[(int64_t)node * ENF_H + n] = z;
+                    if (z4 != nullptr && node < N) z4[(int64_t)node * ENF_H + n] = z;      // kept for the backward pass only
                     x[j] = z * tc::sigmoid_sfu(z);
                 }
                 put8<SPLIT>(IN, tc::img_chunk_offset(n, 4 * cg + ch), tc::IMG_BYTES, x);        // x4^T over the IN image
